@@ -1,0 +1,141 @@
+/*
+ * mgpu.h -- the thin C-ABI between the C++ host side of micropp-b200 and its sm_100a CUDA kernels.
+ *
+ * North star (BASELINE.json): "Host code stays C++ and calls CUDA through a thin C-ABI layer."
+ * Every function below is `extern "C"`, takes plain pointers / sizes, and either manages device
+ * memory of a context or enqueues exactly one kernel (or one small copy) on the context stream.
+ * The orchestration (wave scheduling, Newton loop, CG loop, GP state machine) lives in C++
+ * (micropp_b200/csrc/micropp_host.cpp) and only talks to the GPU through these entry points.
+ *
+ * Reference functions each launcher replaces (file:line under the reference tree):
+ *   mgpu_set_bc          set_displ_bc            src/micro3D.cpp:27-78
+ *   mgpu_asm_rhs         assembly_rhs            src/assembly.cpp:28-103, get_elem_rhs :124-138
+ *   mgpu_asm_mat         assembly_mat            src/assembly.cpp:106-121, get_elem_mat :141-178,
+ *                        ell_add_3D / ell_set_bc_3D  src/ell-common.cpp:166-198, :238-297
+ *   mgpu_cg_init / mgpu_cg_spmv_dot / mgpu_cg_update / mgpu_cg_pupdate
+ *                        ell_solve_cgpd, ell_mvp, get_dot   src/ell.cpp:35-122
+ *   mgpu_axpy_u          u += du                 src/solve.cpp:73
+ *   mgpu_ave_stress      calc_ave_stress         src/average.cpp:58-82
+ *   mgpu_vars_new        calc_vars_new           src/update.cpp:33-56
+ *
+ * Device data layout (all FP64):
+ *   vectors  : per slot, structure-of-arrays by displacement component: v[d*nn_pad + node]
+ *   matrix   : per slot, 243 planes of nn_pad doubles: A[(nbr*9 + fi*3 + fj)*nn_pad + node]
+ *              (nbr = 27-point stencil slot of src/ell-common.cpp:102-130; column indices implicit)
+ *   int.vars : per Gauss point of the macro mesh, v[(var*8 + gp)*nelem_pad + elem], var < nvar
+ */
+#ifndef MGPU_H
+#define MGPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgpu_ctx mgpu_ctx;
+
+/* Per-slot solver state, mirrored on the host after mgpu_fetch_state. */
+typedef struct mgpu_slot_state {
+  double norm0, norm;           /* Newton residual norms (src/solve.cpp:39-41,75) */
+  double rz, pAp, alpha, beta;  /* CG scalars (src/ell.cpp:86-116) */
+  double pnorm0, pnorm;
+  int nr_its, solver_its, nr_active, converged; /* newton_t (include/types.hpp:29-41) */
+  int cg_its, cg_active;
+  int nl_flag;                  /* OR of material->evolute() (src/update.cpp:49) */
+  unsigned ticket;              /* last-block-done counter */
+} mgpu_slot_state;
+
+typedef struct mgpu_config {
+  int nx, ny, nz;
+  int device;                 /* CUDA device ordinal */
+  int ngp;                    /* macro Gauss points that own FE state (u_n,u_k) */
+  const int *elem_type;       /* [nelem] host, values 0..2 (src/micropp.cpp:117-124) */
+  double dsh[8][24];          /* shape derivatives per Gauss point (src/micro3D.cpp:82-98) */
+  double wg;                  /* Gauss weight (src/micropp.cpp:57) */
+  double dx, dy, dz;
+  double mat[3][8];           /* E,nu,Ka,Sy,k,mu,lambda,Xt per material */
+  int mat_type[3];
+  const double *ke_elastic;   /* [3][576] element matrices of the elastic materials (host) */
+  int nr_max_its;
+  double nr_max_tol, nr_rel_tol;
+  int cg_max_its;
+  double cg_abs_tol, cg_rel_tol;
+  int wave_cap;               /* max slots (0 = size from free HBM) */
+} mgpu_config;
+
+/* ---- context ---- */
+int mgpu_device_count(void);
+mgpu_ctx *mgpu_create(const mgpu_config *cfg);
+void mgpu_destroy(mgpu_ctx *);
+int mgpu_wave_size(const mgpu_ctx *);
+int mgpu_nn_pad(const mgpu_ctx *);
+int mgpu_nelem_pad(const mgpu_ctx *);
+int mgpu_nvar(const mgpu_ctx *);
+void mgpu_sync(mgpu_ctx *);
+unsigned long long mgpu_launch_count(const mgpu_ctx *);
+
+/* ---- per-GP persistent state ---- */
+void mgpu_gp_swap(mgpu_ctx *, int gp);              /* update_vars: pointer swaps (include/gp.hpp:95-105) */
+int mgpu_gp_has_vars(const mgpu_ctx *, int gp);
+void mgpu_gp_alloc_vars(mgpu_ctx *, int gp);        /* gp_t::allocate (include/gp.hpp:86-93): zeroed */
+/* reference-layout (AoS) import/export of u_n/u_k (which: 0=n,1=k) and vars_n/vars_k */
+void mgpu_gp_get_u(mgpu_ctx *, int gp, int which, double *host_aos);
+void mgpu_gp_set_u(mgpu_ctx *, int gp, int which, const double *host_aos);
+void mgpu_gp_get_vars(mgpu_ctx *, int gp, int which, double *host_ref_layout);
+void mgpu_gp_set_vars(mgpu_ctx *, int gp, int which, const double *host_ref_layout);
+
+/* ---- wave set-up: bind slots to GPs / strains ---- */
+/* slot_gp[i] >= 0 binds vars_old/new of that GP (vars_mode: 0 none(nullptr), 1 vars_n, ...) */
+void mgpu_bind_slots(mgpu_ctx *, int n, const int *slots, const int *gps, const int *use_vars_old);
+void mgpu_set_slot_strain(mgpu_ctx *, int n, const int *slots, const double *eps6);
+void mgpu_set_list(mgpu_ctx *, int which_list, int n, const int *slots); /* upload an explicit slot list */
+
+/* ---- kernels (each: one launch over list `which_list`, first `n` entries) ---- */
+void mgpu_load_u(mgpu_ctx *, int which_list, int n, int which_u);   /* u_slot <- u_n / u_k of bound GP */
+void mgpu_store_u(mgpu_ctx *, int which_list, int n, int which_u);  /* u_k of bound GP <- u_slot */
+void mgpu_zero_u(mgpu_ctx *, int which_list, int n);                /* u_slot <- 0 */
+void mgpu_set_bc(mgpu_ctx *, int which_list, int n);
+void mgpu_asm_rhs(mgpu_ctx *, int which_list, int n, int mode);     /* mode 0: first of a Newton solve, 1: after update, 2: plain */
+void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_shared: assemble slot list[0] into the shared A0 buffer */
+void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
+void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);
+void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitrary matrix: boundary rows read too */
+void mgpu_cg_update(mgpu_ctx *, int which_list, int n);
+void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
+void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);
+void mgpu_ave_stress(mgpu_ctx *, int which_list, int n);
+void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);
+/* compaction: list_out <- entries of list_in whose (mode 0: nr_active, 1: cg_active) flag is set; returns count (syncs) */
+int mgpu_compact(mgpu_ctx *, int list_in, int n_in, int list_out, int mode);
+
+/* ---- results ---- */
+void mgpu_fetch_state(mgpu_ctx *, int n, const int *slots, mgpu_slot_state *out); /* syncs */
+void mgpu_fetch_stress(mgpu_ctx *, int n, const int *slots, double *sig6);        /* syncs */
+void mgpu_clear_nl_flags(mgpu_ctx *, int which_list, int n);
+
+/* ---- staging (host-pointer versions of the protected micropp<3> kernels; slot 0) ---- */
+void mgpu_stage_put_u(mgpu_ctx *, int slot, const double *host_aos);
+void mgpu_stage_get_u(mgpu_ctx *, int slot, double *host_aos);
+void mgpu_stage_get_vec(mgpu_ctx *, int slot, int which /*0=b,1=du,2=Ap,3=p*/, double *host_aos);
+void mgpu_stage_put_vec(mgpu_ctx *, int slot, int which, const double *host_aos);
+void mgpu_stage_put_vars(mgpu_ctx *, int slot, int which /*0=old,1=new*/, const double *host_ref_layout); /* NULL unbinds */
+void mgpu_stage_get_vars_new(mgpu_ctx *, int slot, double *host_ref_layout);
+void mgpu_stage_get_mat(mgpu_ctx *, int slot, double *vals_ref_layout /* [3nn][81] */);
+void mgpu_stage_put_mat(mgpu_ctx *, int slot, const double *vals_ref_layout);
+void mgpu_ell_cols(int nx, int ny, int nz, int *cols /* [3nn][81] */, int device); /* regenerates src/ell-common.cpp:34-139 on the GPU */
+
+/* ---- measurement ---- */
+void mgpu_prof_enable(mgpu_ctx *, int on);
+/* accumulated since last reset: [0]=spmv ms, [1]=spmv launches, [2]=spmv slot-applications, [3]=asm_mat ms,
+   [4]=asm_rhs ms, [5]=cg_update+pupdate ms */
+void mgpu_prof_read(mgpu_ctx *, double *out6, int reset);
+void mgpu_timer_start(mgpu_ctx *);
+float mgpu_timer_stop(mgpu_ctx *); /* ms on the context stream (syncs) */
+/* isolated SpMV micro-benchmark on the first n slots of the pool (matrix contents as they are) */
+float mgpu_bench_spmv(mgpu_ctx *, int n, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,85 @@
+/*
+ * micropp_b200_ext.h -- additive C entry points next to the reference-compatible micropp_c.h.
+ *
+ * The reference C wrapper cannot set most of micropp_params_t (src/micropp_c.cpp:37-60 hard-codes
+ * them), and the FE stages of micropp<3> are `protected` C++ members that the reference's own tests
+ * reach by subclassing (test/test_cg.cpp:38-82).  These functions expose both to C / ctypes so that
+ * the parity tests and bench.py can drive every stage of the hot path THROUGH THE C-ABI.
+ * All pointers are host pointers in the reference's layouts (u: node*3+d; vars: e*56+gp*7+v;
+ * ELL values: row*81+slot).
+ */
+#ifndef MICROPP_B200_EXT_H
+#define MICROPP_B200_EXT_H
+
+#include "micropp_c.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Flat mirror of micropp_params_t (include/types.hpp). */
+struct micropp3_params {
+  int ngp;
+  int size[3];
+  int type;
+  double geo_params[4];
+  int mat_type[3];
+  double mat_E[3], mat_nu[3], mat_Ka[3], mat_Sy[3], mat_Xt[3];
+  const int *coupling; /* NULL => every GP is FE_ONE_WAY (src/micropp.cpp:88-96) */
+  int subiterations;
+  int nsubiterations;
+  int mpi_rank;
+  int nr_max_its;
+  double nr_max_tol;
+  double nr_rel_tol;
+  int calc_ctan_lin;
+  int use_A0;
+  int its_with_A0;
+  int lin_stress;
+  int write_log;
+};
+
+void micropp3_new_ext(struct micropp3 *self, const struct micropp3_params *params);
+
+/* batched boundary crossing: one call for all GPs (strain: ngp*6; stress: ngp*6; ctan: ngp*36) */
+void micropp3_set_strains(struct micropp3 *self, const double *strain);
+void micropp3_get_stresses(const struct micropp3 *self, double *stress);
+void micropp3_get_ctans(const struct micropp3 *self, double *ctan);
+
+/* inspection */
+int micropp3x_nelem(const struct micropp3 *self);
+int micropp3x_nndim(const struct micropp3 *self);
+int micropp3x_wave_size(const struct micropp3 *self);
+void micropp3x_get_elem_type(const struct micropp3 *self, int *out);
+void micropp3x_get_bmat(const struct micropp3 *self, double *out /* [8][6][24] */);
+void micropp3x_get_ctan_lin(const struct micropp3 *self, double *out36);
+int micropp3x_get_u(const struct micropp3 *self, int gp, int which /*0=u_n,1=u_k*/, double *out);
+int micropp3x_get_vars(const struct micropp3 *self, int gp, int which /*0=vars_n,1=vars_k*/, double *out);
+
+/* FE stages (protected members of the reference class) */
+void micropp3x_set_displ_bc(struct micropp3 *self, const double *eps, double *u);
+double micropp3x_assembly_rhs(struct micropp3 *self, const double *u, const double *vars_old, double *b);
+void micropp3x_assembly_mat(struct micropp3 *self, const double *u, const double *vars_old, double *vals);
+void micropp3x_newton(struct micropp3 *self, const double *eps, const double *vars_old, double *u, int *out3);
+void micropp3x_ave_stress(struct micropp3 *self, const double *u, const double *vars_old, double *sig);
+int micropp3x_vars_new(struct micropp3 *self, const double *u, const double *vars_old, double *vars_new);
+
+/* ELL pieces */
+void micropp3x_ell_cols(int nx, int ny, int nz, int *cols);
+void micropp3x_ell_mvp(int nx, int ny, int nz, const double *vals, const double *x, double *y);
+int micropp3x_ell_solve_cgpd(int nx, int ny, int nz, const double *vals, const double *b, double *x, double *err);
+void micropp3x_elem_nodes(int nx, int ny, int ex, int ey, int ez, int *n8);
+/* colour of an element in the 8-colour structured ordering: (ex&1) + 2(ey&1) + 4(ez&1) */
+int micropp3x_elem_colour(int ex, int ey, int ez);
+
+/* measurement (CUDA events on the library's own stream) */
+void micropp3x_prof_enable(struct micropp3 *self, int on);
+void micropp3x_prof_read(struct micropp3 *self, double *out6, int reset);
+double micropp3x_last_homogenize_ms(const struct micropp3 *self);
+unsigned long long micropp3x_launch_count(const struct micropp3 *self);
+double micropp3x_bench_spmv(struct micropp3 *self, int nslots, int iters); /* ms per launch */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,335 @@
+// ell_host.cpp -- the reference's host-level ELL API (include/ell.hpp) and hex8 helpers
+// (include/common.hpp) for code that calls them directly (test/test_ell_2.cpp, test/test_cg.cpp,
+// test/test_get_elem_nodes.cpp).
+//
+// Index structures (column table, element scatter map, boundary rows) are integer work done on the
+// host exactly as the reference defines them.  The two numerical entry points, ell_mvp and
+// ell_solve_cgpd, stage the host matrix into the device plane layout and run the same CUDA kernels
+// as homogenize() (generic variant: boundary rows are read, not assumed to be identity rows).
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <tuple>
+
+#include "common.hpp"
+#include "ell.hpp"
+#include "fe_math.cuh"
+#include "mgpu.h"
+#include "micropp_b200_ext.h"
+#include "mpp_engine.hpp"
+
+using namespace std;
+
+// ---- hex8 helpers -----------------------------------------------------------------------------
+void get_elem_nodes(int n[8], const int nx, const int ny, const int ex, const int ey, const int ez) {
+  const int base = (ez * ny + ey) * nx + ex;
+  for (int a = 0; a < 8; ++a) n[a] = base + corner_x(a) + corner_y(a) * nx + corner_z(a) * nx * ny;
+}
+
+void get_elem_displ(const double *u, double elem_disp[NPE * DIM], int nx, int ny, int ex, int ey, int ez) {
+  int n[NPE];
+  get_elem_nodes(n, nx, ny, ex, ey, ez);
+  for (int a = 0; a < NPE; ++a)
+    for (int d = 0; d < DIM; ++d) elem_disp[a * DIM + d] = u[n[a] * DIM + d];
+}
+
+void get_strain(const double *u, int gp, double *strain_gp, const double bmat[NPE][NVOI][NPE * DIM], int nx, int ny,
+                int ex, int ey, int ez) {
+  double ue[NPE * DIM];
+  get_elem_displ(u, ue, nx, ny, ex, ey, ez);
+  for (int v = 0; v < NVOI; ++v) {
+    double acc = 0;
+    for (int i = 0; i < NPE * DIM; ++i) acc += bmat[gp][v][i] * ue[i];
+    strain_gp[v] = acc;
+  }
+}
+
+// ---- structure ------------------------------------------------------------------------------------
+void ell_init(ell_matrix *m, const int nfield, const int dim, const int ns[3], const double min_err,
+              const double rel_err, const int max_its) {
+  assert(dim == 2 || dim == 3);
+  assert(nfield > 0 && max_its > 0 && min_err > 0);
+  memcpy(m->n, ns, 3 * sizeof(int));
+  const int nx = ns[0], ny = ns[1], nz = (dim == 3) ? ns[2] : 1;
+  const int stencil = (dim == 2) ? 9 : 27;
+  m->dim = dim;
+  m->nfield = nfield;
+  m->nn = nx * ny * nz;
+  m->shift = stencil / 2;  // slot of the node itself: 4 or 13
+  m->nnz = stencil * nfield;
+  m->nrow = m->ncol = m->nn * nfield;
+  m->max_its = max_its;
+  m->min_err = min_err;
+  m->rel_err = rel_err;
+  const size_t nval = (size_t)m->nnz * m->nrow;
+  m->cols = (int *)malloc(nval * sizeof(int));
+  m->vals = (double *)malloc(nval * sizeof(double));
+  double **work[5] = {&m->k, &m->r, &m->z, &m->p, &m->Ap};
+  for (auto w : work) *w = (double *)malloc((size_t)m->nrow * sizeof(double));
+
+  // Row (node, fi) lists its 9/27 stencil neighbours in (dz, dy, dx) order, nfield columns each;
+  // a neighbour outside the grid is recorded as node 0 (its value stays 0).  src/ell-common.cpp:70-137.
+  const int kmin = (dim == 3) ? -1 : 0, kmax = (dim == 3) ? 1 : 0;
+  for (int zi = 0; zi < nz; ++zi)
+    for (int yi = 0; yi < ny; ++yi)
+      for (int xi = 0; xi < nx; ++xi) {
+        const int ni = (zi * ny + yi) * nx + xi;
+        for (int fi = 0; fi < nfield; ++fi) {
+          int *row = m->cols + ((size_t)ni * nfield + fi) * m->nnz;
+          int s = 0;
+          for (int dk = kmin; dk <= kmax; ++dk)
+            for (int dj = -1; dj <= 1; ++dj)
+              for (int di = -1; di <= 1; ++di, ++s) {
+                const int x = xi + di, y = yi + dj, z = zi + dk;
+                const bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
+                const int nb = in ? (z * ny + y) * nx + x : 0;
+                for (int fj = 0; fj < nfield; ++fj) row[s * nfield + fj] = nb * nfield + fj;
+              }
+        }
+      }
+}
+
+void ell_free(ell_matrix *m) {
+  free(m->cols);
+  free(m->vals);
+  free(m->k);
+  free(m->r);
+  free(m->z);
+  free(m->p);
+  free(m->Ap);
+  m->cols = NULL;
+  m->vals = NULL;
+  m->k = m->r = m->z = m->p = m->Ap = NULL;
+}
+
+void ell_set_zero_mat(ell_matrix *m) { memset(m->vals, 0, (size_t)m->nrow * m->nnz * sizeof(double)); }
+
+// Scatter of one element matrix (src/ell-common.cpp:141-198).  Entry (local node i, field fi) x
+// (local node j, field fj) goes to row (node_i, fi), slot cols_row(i,j)*nfield + fj.
+void ell_add_3D(ell_matrix *m, int ex, int ey, int ez, const double *Ae) {
+  const int nx = m->n[0], ny = m->n[1], nf = m->nfield, nnz = m->nnz;
+  int nodes[8];
+  get_elem_nodes(nodes, nx, ny, ex, ey, ez);
+  for (int fi = 0; fi < nf; ++fi)
+    for (int fj = 0; fj < nf; ++fj)
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j)
+          m->vals[((size_t)nodes[i] * nf + fi) * nnz + cols_row(i, j) * nf + fj] +=
+              Ae[(i * nf + fi) * 8 * nf + j * nf + fj];
+}
+
+void ell_add_2D(ell_matrix *m, int ex, int ey, const double *Ae) {
+  const int nx = m->n[0], nf = m->nfield, nnz = m->nnz;
+  const int n0 = ey * nx + ex;
+  const int nodes[4] = {n0, n0 + 1, n0 + nx + 1, n0 + nx};
+  const int cx[4] = {0, 1, 1, 0}, cy[4] = {0, 0, 1, 1};
+  for (int fi = 0; fi < nf; ++fi)
+    for (int fj = 0; fj < nf; ++fj)
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          const int slot = (cy[j] - cy[i] + 1) * 3 + (cx[j] - cx[i] + 1);
+          m->vals[((size_t)nodes[i] * nf + fi) * nnz + slot * nf + fj] += Ae[(i * nf + fi) * 4 * nf + j * nf + fj];
+        }
+}
+
+namespace {
+inline void identity_row(ell_matrix *m, int node, int d) {
+  double *row = m->vals + ((size_t)node * m->nfield + d) * m->nnz;
+  memset(row, 0, m->nnz * sizeof(double));
+  row[m->shift * m->nfield + d] = 1;
+}
+}  // namespace
+
+// Dirichlet rows on the boundary of the grid become identity rows; columns are left untouched
+// (src/ell-common.cpp:202-297).
+void ell_set_bc_3D(ell_matrix *m) {
+  const int nx = m->n[0], ny = m->n[1], nz = m->n[2];
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i)
+        if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1 || k == 0 || k == nz - 1)
+          for (int d = 0; d < m->nfield; ++d) identity_row(m, (k * ny + j) * nx + i, d);
+}
+
+void ell_set_bc_2D(ell_matrix *m) {
+  const int nx = m->n[0], ny = m->n[1];
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i)
+      if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1)
+        for (int d = 0; d < m->nfield; ++d) identity_row(m, j * nx + i, d);
+}
+
+// ---- tiny host reductions (API completeness) --------------------------------------------------------
+double get_norm(const double *v, const int n) {
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) acc += v[i] * v[i];
+  return sqrt(acc);
+}
+double get_dot(const double *a, const double *b, const int n) {
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) acc += a[i] * b[i];
+  return acc;
+}
+double ell_get_norm(const ell_matrix *m) {
+  double acc = 0.0;
+  const size_t n = (size_t)m->nrow * m->nnz;
+  for (size_t i = 0; i < n; ++i) acc += m->vals[i];
+  return sqrt(acc);
+}
+
+int ell_write(string filename, const ell_matrix *A) {
+  ofstream f(filename, ios::out | ios::binary);
+  if (!f) {
+    cout << "Cannot open file:" << filename << endl;
+    return 1;
+  }
+  f.write((const char *)A, sizeof(ell_matrix));
+  f.write((const char *)A->vals, (size_t)A->nrow * A->nnz * sizeof(double));
+  f.write((const char *)A->cols, (size_t)A->nrow * A->nnz * sizeof(int));
+  return 0;
+}
+int ell_read(string filename, ell_matrix *A) {
+  ifstream f(filename, ios::in | ios::binary);
+  if (!f) {
+    cout << "Cannot open file:" << filename << endl;
+    return 1;
+  }
+  int *cols = A->cols;
+  double *vals = A->vals;
+  f.read((char *)A, sizeof(ell_matrix));
+  A->cols = cols;
+  A->vals = vals;
+  f.read((char *)A->vals, (size_t)A->nrow * A->nnz * sizeof(double));
+  f.read((char *)A->cols, (size_t)A->nrow * A->nnz * sizeof(int));
+  return 0;
+}
+void print_ell(const ell_matrix *A) {
+  FILE *f = fopen("A.dat", "w");
+  for (int i = 0; i < A->nrow; ++i)
+    for (int j = 0; j < A->nnz; ++j) fprintf(f, "[%d][%d][%lf]\n", i, A->cols[i * A->nnz + j], A->vals[i * A->nnz + j]);
+  fclose(f);
+}
+
+// ---- GPU-backed SpMV / DPCG on a host matrix --------------------------------------------------------
+namespace {
+
+struct EllDev {
+  mpp_engine eng;
+};
+
+// one cached single-slot context per (grid, tolerances); intentionally never destroyed (process lifetime)
+EllDev *ell_device(const int n[3], int max_its, double min_err, double rel_err) {
+  typedef std::tuple<int, int, int, int, double, double> key_t;
+  static std::map<key_t, EllDev *> cache;
+  const key_t key(n[0], n[1], n[2], max_its, min_err, rel_err);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  mgpu_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.nx = n[0];
+  cfg.ny = n[1];
+  cfg.nz = n[2];
+  cfg.device = 0;
+  cfg.ngp = 0;
+  const int nelem = std::max(1, (n[0] - 1) * (n[1] - 1) * (n[2] - 1));
+  std::vector<int> et(nelem, 0);
+  std::vector<double> ke(3 * 576, 0.0);
+  cfg.elem_type = et.data();
+  cfg.ke_elastic = ke.data();
+  cfg.wg = 1.0;
+  cfg.dx = cfg.dy = cfg.dz = 1.0;
+  cfg.nr_max_its = 1;
+  cfg.nr_max_tol = 1e-10;
+  cfg.nr_rel_tol = 1e-3;
+  cfg.cg_max_its = max_its;
+  cfg.cg_abs_tol = min_err;
+  cfg.cg_rel_tol = rel_err;
+  cfg.wave_cap = 1;
+  EllDev *d = new EllDev();
+  d->eng.ctx = mgpu_create(&cfg);
+  d->eng.W = 1;
+  cache[key] = d;
+  return d;
+}
+
+void require_3d(const ell_matrix *m, const char *who) {
+  if (m->dim != 3 || m->nfield != 3) {
+    fprintf(stderr, "micropp-b200: %s is provided for the 3-D, 3-field ELL of the hot path only (dim=%d nfield=%d)\n",
+            who, m->dim, m->nfield);
+    abort();
+  }
+}
+
+}  // namespace
+
+void ell_mvp(const ell_matrix *m, const double *x, double *y) {
+  require_3d(m, "ell_mvp");
+  EllDev *d = ell_device(m->n, m->max_its > 0 ? m->max_its : CG_MAX_ITS, m->min_err > 0 ? m->min_err : CG_ABS_TOL,
+                         m->rel_err);
+  const int s0 = 0;
+  mgpu_ctx *ctx = d->eng.ctx;
+  mgpu_set_list(ctx, mpp_engine::L_SUB, 1, &s0);
+  mgpu_stage_put_mat(ctx, 0, m->vals);
+  mgpu_stage_put_vec(ctx, 0, 3, x);  // p <- x
+  mgpu_spmv_generic(ctx, mpp_engine::L_SUB, 1, 1);
+  mgpu_stage_get_vec(ctx, 0, 2, y);  // y <- Ap
+}
+
+int ell_solve_cgpd(const ell_matrix *m, const double *b, double *x, double *err) {
+  if (!m || !b || !x) return 1;
+  require_3d(m, "ell_solve_cgpd");
+  EllDev *d = ell_device(m->n, m->max_its, m->min_err, m->rel_err);
+  const int s0 = 0;
+  mgpu_ctx *ctx = d->eng.ctx;
+  mgpu_set_list(ctx, mpp_engine::L_SUB, 1, &s0);
+  mgpu_stage_put_mat(ctx, 0, m->vals);
+  mgpu_stage_put_vec(ctx, 0, 0, b);
+  d->eng.cg_solve(mpp_engine::L_SUB, 1, 0, true);
+  mgpu_stage_get_vec(ctx, 0, 1, x);
+  mgpu_slot_state st;
+  mgpu_fetch_state(ctx, 1, &s0, &st);
+  if (err) *err = st.rz;
+  return st.cg_its;
+}
+
+// ---- C-ABI extension: ELL pieces -----------------------------------------------------------------------
+extern "C" {
+
+void micropp3x_ell_cols(int nx, int ny, int nz, int *cols) { mgpu_ell_cols(nx, ny, nz, cols, 0); }
+
+void micropp3x_ell_mvp(int nx, int ny, int nz, const double *vals, const double *x, double *y) {
+  ell_matrix A;
+  memset(&A, 0, sizeof(A));
+  A.n[0] = nx;
+  A.n[1] = ny;
+  A.n[2] = nz;
+  A.dim = 3;
+  A.nfield = 3;
+  A.max_its = CG_MAX_ITS;
+  A.min_err = CG_ABS_TOL;
+  A.rel_err = CG_REL_TOL;
+  A.vals = const_cast<double *>(vals);
+  ell_mvp(&A, x, y);
+}
+
+int micropp3x_ell_solve_cgpd(int nx, int ny, int nz, const double *vals, const double *b, double *x, double *err) {
+  ell_matrix A;
+  memset(&A, 0, sizeof(A));
+  A.n[0] = nx;
+  A.n[1] = ny;
+  A.n[2] = nz;
+  A.dim = 3;
+  A.nfield = 3;
+  A.max_its = CG_MAX_ITS;
+  A.min_err = CG_ABS_TOL;
+  A.rel_err = CG_REL_TOL;
+  A.vals = const_cast<double *>(vals);
+  return ell_solve_cgpd(&A, b, x, err);
+}
+
+void micropp3x_elem_nodes(int nx, int ny, int ex, int ey, int ez, int *n8) { get_elem_nodes(n8, nx, ny, ex, ey, ez); }
+
+int micropp3x_elem_colour(int ex, int ey, int ez) { return (ex & 1) + 2 * (ey & 1) + 4 * (ez & 1); }
+}

@@ -1,0 +1,1620 @@
+// mgpu_kernels.cu -- hand-written sm_100a kernels of the RVE-homogenization hot path and the
+// thin C-ABI (include/mgpu.h) that launches them.  FP64 throughout; no tensor cores (no stage is
+// a dense contraction); every kernel is either HBM-bound (SpMV / CG vector updates / gather
+// assembly of elastic RVEs) or FP64-pipe-bound (forward-difference tangent + B^T C B).
+//
+// Design in one paragraph: a *wave* of W RVEs (one per macro Gauss point) is resident in HBM.
+// Every kernel is launched over (node- or element-blocks) x (a compacted list of slots), so one
+// launch advances all RVEs of the wave by one algorithmic step.  Per-slot scalars (CG alpha/beta,
+// norms, iteration counters, convergence flags) never leave the device inside a solve: the last
+// block of each reducing kernel (ticket counter) folds the per-block partial sums in a fixed order
+// and applies the reference's scalar logic (src/ell.cpp:86-119, src/solve.cpp:43-78).  Reductions
+// are therefore deterministic and there is not a single floating-point atomic in the file.
+//
+// Assembly is a *gather by node* instead of the reference's element scatter: each ELL value is
+// written exactly once, coalesced, with the element contributions added in the reference's element
+// visiting order -- no atomics, no colours, no read-modify-write traffic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fe_math.cuh"
+#include "mgpu.h"
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      fprintf(stderr, "micropp-b200: CUDA error '%s' at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, \
+              __LINE__, #call);                                                                          \
+      abort();                                                                                           \
+    }                                                                                                    \
+  } while (0)
+
+namespace {
+
+constexpr int NT = 128;      // threads per block of node/element kernels
+constexpr int NPLANE = 243;  // 27 neighbours x 3 x 3
+constexpr int NLIST = 6;
+constexpr int NRED = 6;      // max values reduced per kernel
+
+struct MeshConst {
+  int nx, ny, nz, nxny, nn, nn_pad;
+  int nex, ney, nez, nelem, nelem_pad;
+  int nvar;
+  int nr_max_its, cg_max_its;
+  double dx, dy, dz, wg;
+  double nr_max_tol, nr_rel_tol, cg_abs_tol, cg_rel_tol;
+  double dsh[8][24];
+  mpp_material mat[3];
+};
+
+struct SlotTables {  // device arrays, one entry per slot
+  mgpu_slot_state *state;
+  const double **vars_old;
+  double **vars_new;
+  double **u_n;
+  double **u_k;
+  double *eps;     // [W][6]
+  double *stress;  // [W][6]
+  double *partial; // [W][NRED][nblk_max]
+  int nblk_max;
+};
+
+struct VecPool {
+  double *u, *b, *du, *k, *r, *z, *p, *Ap;  // [W][3*nn_pad]
+  double *mat;                              // [W][243*nn_pad]
+  double *mat_shared;                       // [243*nn_pad] (A0)
+  size_t vstride, mstride;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void node_ijk(const MeshConst &P, int n, int &i, int &j, int &k) {
+  k = n / P.nxny;
+  const int r = n - k * P.nxny;
+  j = r / P.nx;
+  i = r - j * P.nx;
+}
+__device__ __forceinline__ bool on_boundary(const MeshConst &P, int i, int j, int k) {
+  return i == 0 || i == P.nx - 1 || j == 0 || j == P.ny - 1 || k == 0 || k == P.nz - 1;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum NV values over the block; result valid in thread 0.  Fixed tree => deterministic.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *sm /* [NV][NT/32] */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const double s = warp_sum(v[q]);
+    if (lane == 0) sm[q * (NT / 32) + w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < NT / 32; ++ww) s += sm[q * (NT / 32) + ww];
+      v[q] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-wide deterministic reduction with a ticket: every block deposits its partial sums; the block
+// that draws the last ticket re-reduces all partials in a fixed order.  Returns true in every thread
+// of that last block; totals valid in its thread 0.
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partial, int pstride, unsigned *ticket, double *sm,
+                                         int *sflag) {
+  block_sum<NV>(v, sm);
+  const int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) partial[q * pstride + blockIdx.x] = v[q];
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    *sflag = (t == (unsigned)(nblk - 1));
+  }
+  __syncthreads();
+  if (!*sflag) return false;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += NT) acc += __ldcg(&partial[q * pstride + b]);
+    v[q] = acc;
+  }
+  block_sum<NV>(v, sm);
+  if (threadIdx.x == 0) *ticket = 0u;
+  return true;
+}
+
+__device__ __forceinline__ const double *fetch_vars(const double *vbase, int nelem_pad, int e, int gp, int nv,
+                                                    double *buf) {
+  if (!vbase) return nullptr;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) buf[q] = (q < nv) ? __ldg(&vbase[(size_t)(q * 8 + gp) * nelem_pad + e]) : 0.0;
+  return buf;
+}
+
+__device__ __forceinline__ void gather_ue(const MeshConst &P, const double *__restrict__ u, int ex, int ey, int ez,
+                                          double *ue) {
+  const int n0 = ez * P.nxny + ey * P.nx + ex;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int nd = n0 + corner_x(a) + corner_y(a) * P.nx + corner_z(a) * P.nxny;  // src/common.cpp:30-41
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ue[a * 3 + d] = u[(size_t)d * P.nn_pad + nd];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// u <- u_n / u_k ; u_k <- u
+// ------------------------------------------------------------------------------------------------
+__global__ void k_load_u(MeshConst P, const int *__restrict__ list, SlotTables T, double *u_pool, size_t vstride,
+                         int which) {
+  const int slot = list[blockIdx.y];
+  const double *src = which ? T.u_k[slot] : T.u_n[slot];
+  double *dst = u_pool + (size_t)slot * vstride;
+  const int len = 3 * P.nn_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_store_u(MeshConst P, const int *__restrict__ list, SlotTables T, const double *u_pool,
+                          size_t vstride, int which) {
+  const int slot = list[blockIdx.y];
+  double *dst = which ? T.u_k[slot] : T.u_n[slot];
+  const double *src = u_pool + (size_t)slot * vstride;
+  const int len = 3 * P.nn_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_zero_u(MeshConst P, const int *__restrict__ list, double *u_pool, size_t vstride) {
+  const int slot = list[blockIdx.y];
+  double *dst = u_pool + (size_t)slot * vstride;
+  const int len = 3 * P.nn_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// set_displ_bc (src/micro3D.cpp:27-78)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_set_bc(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+                         double *u_pool, size_t vstride) {
+  const int slot = list[blockIdx.y];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= P.nn) return;
+  int i, j, k;
+  node_ijk(P, n, i, j, k);
+  if (!on_boundary(P, i, j, k)) return;
+  double eps[6], c[3], u3[3];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) eps[q] = T.eps[slot * 6 + q];
+  bc_coords(i, j, k, P.nx, P.ny, P.nz, P.dx, P.dy, P.dz, c);
+  bc_displacement(eps, c, u3);
+  double *u = u_pool + (size_t)slot * vstride;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) u[(size_t)d * P.nn_pad + n] = u3[d];
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly_rhs (src/assembly.cpp:28-103): gather by node, elements visited in (ez,ey,ex) order.
+// ------------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ void elem_rhs_at_node(const MeshConst &P, const double *__restrict__ u,
+                                                 const double *vars, const int *__restrict__ elem_type, int ex,
+                                                 int ey, int ez, double &bx, double &by, double &bz) {
+  double ue[24];
+  gather_ue(P, u, ex, ey, ez, ue);
+  const int e = (ez * P.ney + ey) * P.nex + ex;
+  const int type = __ldg(&elem_type[e]);
+  const mpp_material m = P.mat[type];
+  const int nv = mat_nvar(m.type);
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  const double wg = P.wg;
+#pragma unroll 1
+  for (int gp = 0; gp < 8; ++gp) {
+    double eps[6], sig[6], vbuf[7];
+    gp_strain(P.dsh[gp], ue, eps);
+    const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+    mat_stress(m, eps, v, sig);
+    const double gx = P.dsh[gp][A * 3 + 0], gy = P.dsh[gp][A * 3 + 1], gz = P.dsh[gp][A * 3 + 2];
+    // be[i] += B[gp][j][i] * sig[j] * wg, j ascending (src/assembly.cpp:135-136)
+    sx += gx * sig[0] * wg;
+    sx += gy * sig[3] * wg;
+    sx += gz * sig[4] * wg;
+    sy += gy * sig[1] * wg;
+    sy += gx * sig[3] * wg;
+    sy += gz * sig[5] * wg;
+    sz += gz * sig[2] * wg;
+    sz += gx * sig[4] * wg;
+    sz += gy * sig[5] * wg;
+  }
+  bx += sx;
+  by += sy;
+  bz += sz;
+}
+
+// mode 0: first residual of a Newton solve (sets norm0, its=0); 1: after an update (its++); 2: plain
+__global__ void __launch_bounds__(NT)
+    k_asm_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+              const double *__restrict__ u_pool, double *b_pool, size_t vstride, const int *__restrict__ elem_type,
+              int mode) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  if (mode == 1 && !st->nr_active) return;
+  const double *u = u_pool + (size_t)slot * vstride;
+  double *b = b_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double nrm[1] = {0.0};
+  if (n < P.nn) {
+    int i, j, k;
+    node_ijk(P, n, i, j, k);
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    if (!on_boundary(P, i, j, k)) {
+      // the eight elements around the node in the reference's visiting order (ez outer, ex inner)
+      elem_rhs_at_node<corner_of(1, 1, 1)>(P, u, vars, elem_type, i - 1, j - 1, k - 1, bx, by, bz);
+      elem_rhs_at_node<corner_of(0, 1, 1)>(P, u, vars, elem_type, i, j - 1, k - 1, bx, by, bz);
+      elem_rhs_at_node<corner_of(1, 0, 1)>(P, u, vars, elem_type, i - 1, j, k - 1, bx, by, bz);
+      elem_rhs_at_node<corner_of(0, 0, 1)>(P, u, vars, elem_type, i, j, k - 1, bx, by, bz);
+      elem_rhs_at_node<corner_of(1, 1, 0)>(P, u, vars, elem_type, i - 1, j - 1, k, bx, by, bz);
+      elem_rhs_at_node<corner_of(0, 1, 0)>(P, u, vars, elem_type, i, j - 1, k, bx, by, bz);
+      elem_rhs_at_node<corner_of(1, 0, 0)>(P, u, vars, elem_type, i - 1, j, k, bx, by, bz);
+      elem_rhs_at_node<corner_of(0, 0, 0)>(P, u, vars, elem_type, i, j, k, bx, by, bz);
+      bx = -bx;
+      by = -by;
+      bz = -bz;
+    }
+    b[n] = bx;
+    b[(size_t)P.nn_pad + n] = by;
+    b[(size_t)2 * P.nn_pad + n] = bz;
+    nrm[0] = bx * bx + by * by + bz * bz;
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<1>(nrm, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    const double norm = sqrt(nrm[0]);
+    st->norm = norm;
+    if (mode == 2) return;
+    int its;
+    if (mode == 0) {
+      st->norm0 = norm;
+      st->nr_its = its = 0;
+      st->solver_its = 0;
+      st->converged = 0;
+    } else {
+      its = ++st->nr_its;
+    }
+    // loop head of src/solve.cpp:43-47 -- no test once nr_max_its solves have been spent
+    int active = 0;
+    if (its < P.nr_max_its) {
+      if (norm < P.nr_max_tol || norm < st->norm0 * P.nr_rel_tol)
+        st->converged = 1;
+      else
+        active = 1;
+    }
+    st->nr_active = active;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly_mat, all-elastic RVE (src/assembly.cpp:106-178 + src/ell-common.cpp:166-297).
+// Element matrices of elastic materials do not depend on u (src/material.cpp:84-94), so each node
+// gathers its 27 3x3 blocks from a per-material 24x24 table held in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int DI, int DJ, int DK>
+__device__ __forceinline__ void gather_block_elastic(const double *__restrict__ s_ke, const int (&et)[8],
+                                                     double (&acc)[9]) {
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+  // reference element order of assembly_mat: ex outermost, ez innermost (src/assembly.cpp:112-114)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ax = (c >> 2) & 1, ay = (c >> 1) & 1, az = c & 1;  // element = (i-1+ax, j-1+ay, k-1+az)
+    const int lx = 1 - ax, ly = 1 - ay, lz = 1 - az;             // this node inside that element
+    const int mx = lx + DI, my = ly + DJ, mz = lz + DK;          // the neighbour inside that element
+    if (mx >= 0 && mx <= 1 && my >= 0 && my <= 1 && mz >= 0 && mz <= 1) {
+      const int a = corner_of(lx, ly, lz), jn = corner_of(mx, my, mz);
+      const double *ke = s_ke + et[c] * 576;
+#pragma unroll
+      for (int fi = 0; fi < 3; ++fi)
+#pragma unroll
+        for (int fj = 0; fj < 3; ++fj) acc[fi * 3 + fj] += ke[(a * 3 + fi) * 24 + jn * 3 + fj];
+    }
+  }
+}
+
+template <int NBR>
+__device__ __forceinline__ void asm_elastic_slot(const double *__restrict__ s_ke, const int (&et)[8], double *A,
+                                                 size_t nn_pad, int n) {
+  constexpr int DI = NBR % 3 - 1, DJ = (NBR / 3) % 3 - 1, DK = NBR / 9 - 1;
+  double acc[9];
+  gather_block_elastic<DI, DJ, DK>(s_ke, et, acc);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) A[(size_t)(NBR * 9 + q) * nn_pad + n] = acc[q];
+}
+
+template <int NBR>
+struct AsmElasticLoop {
+  static __device__ __forceinline__ void run(const double *__restrict__ s_ke, const int (&et)[8], double *A,
+                                             size_t nn_pad, int n) {
+    asm_elastic_slot<NBR>(s_ke, et, A, nn_pad, n);
+    AsmElasticLoop<NBR + 1>::run(s_ke, et, A, nn_pad, n);
+  }
+};
+template <>
+struct AsmElasticLoop<27> {
+  static __device__ __forceinline__ void run(const double *__restrict__, const int (&)[8], double *, size_t, int) {}
+};
+
+__global__ void __launch_bounds__(NT)
+    k_asm_mat_elastic(const __grid_constant__ MeshConst P, const int *__restrict__ list, double *mat_pool,
+                      size_t mstride, double *mat_shared, const int *__restrict__ elem_type,
+                      const double *__restrict__ ke_tab) {
+  __shared__ double s_ke[3 * 576];
+  for (int q = threadIdx.x; q < 3 * 576; q += NT) s_ke[q] = ke_tab[q];
+  __syncthreads();
+  const int slot = list[blockIdx.y];
+  double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= P.nn) return;
+  int i, j, k;
+  node_ijk(P, n, i, j, k);
+  if (on_boundary(P, i, j, k)) {
+    // ell_set_bc_3D (src/ell-common.cpp:238-297): identity rows
+#pragma unroll 9
+    for (int pl = 0; pl < NPLANE; ++pl) {
+      const int q = pl - 13 * 9;
+      A[(size_t)pl * P.nn_pad + n] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;
+    }
+    return;
+  }
+  int et[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ex = i - 1 + ((c >> 2) & 1), ey = j - 1 + ((c >> 1) & 1), ez = k - 1 + (c & 1);
+    et[c] = __ldg(&elem_type[(ez * P.ney + ey) * P.nex + ex]);
+  }
+  AsmElasticLoop<0>::run(s_ke, et, A, (size_t)P.nn_pad, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly_mat, general (damage / plastic / mixed).  8 threads per node: thread (node, c) owns the
+// element c of the 8 around the node and computes the 3 rows of that element's 24x24 matrix that
+// belong to the node, K_rows = sum_gp (G_a^T C_gp wg) B_gp, with C_gp the reference's forward-
+// difference tangent (src/material.cpp:49-63).  The 8 row blocks are then added into a shared-
+// memory image of the node's ELL row in the reference's element order (ex outermost), and the
+// image is written out coalesced: each ELL value is stored to HBM exactly once.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN = 16;  // nodes per block of the general assembly kernel (GN*8 == NT)
+
+__global__ void __launch_bounds__(NT)
+    k_asm_mat_general(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+                      const double *__restrict__ u_pool, size_t vstride, double *mat_pool, size_t mstride,
+                      double *mat_shared, const int *__restrict__ elem_type, const double *__restrict__ ke_tab) {
+  extern __shared__ double s_acc[];  // [GN][243]
+  const int slot = list[blockIdx.y];
+  const double *u = u_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
+
+  for (int q = threadIdx.x; q < GN * NPLANE; q += NT) s_acc[q] = 0.0;
+  __syncthreads();
+
+  const int ln = threadIdx.x >> 3, c = threadIdx.x & 7;
+  const int n = blockIdx.x * GN + ln;
+  int i = 0, j = 0, k = 0;
+  bool valid = n < P.nn, bnd = false;
+  if (valid) {
+    node_ijk(P, n, i, j, k);
+    bnd = on_boundary(P, i, j, k);
+  }
+  const bool work = valid && !bnd;
+
+  double R[72];
+  int a = 0;
+  if (work) {
+    const int ax = (c >> 2) & 1, ay = (c >> 1) & 1, az = c & 1;
+    const int ex = i - 1 + ax, ey = j - 1 + ay, ez = k - 1 + az;
+    a = corner_of(1 - ax, 1 - ay, 1 - az);
+    const int e = (ez * P.ney + ey) * P.nex + ex;
+    const int type = __ldg(&elem_type[e]);
+    const mpp_material m = P.mat[type];
+    if (m.type == MPP_ELASTIC) {
+      const double *ke = ke_tab + type * 576 + a * 72;
+#pragma unroll
+      for (int q = 0; q < 72; ++q) R[q] = __ldg(&ke[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 72; ++q) R[q] = 0.0;
+      double ue[24];
+      gather_ue(P, u, ex, ey, ez, ue);
+      const int nv = mat_nvar(m.type);
+      const double wg = P.wg;
+#pragma unroll 1
+      for (int gp = 0; gp < 8; ++gp) {
+        double eps[6], C[36], vbuf[7];
+        gp_strain(P.dsh[gp], ue, eps);
+        const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+        mat_ctan(m, eps, v, C);
+        const double gx = P.dsh[gp][a * 3 + 0] * wg, gy = P.dsh[gp][a * 3 + 1] * wg, gz = P.dsh[gp][a * 3 + 2] * wg;
+#pragma unroll
+        for (int fi = 0; fi < 3; ++fi) {
+          // row fi of G_a^T C : non-zero B rows for column 3a+fi (src/micro3D.cpp:100-119)
+          double t[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            if (fi == 0)
+              t[q] = gx * C[0 * 6 + q] + gy * C[3 * 6 + q] + gz * C[4 * 6 + q];
+            else if (fi == 1)
+              t[q] = gy * C[1 * 6 + q] + gx * C[3 * 6 + q] + gz * C[5 * 6 + q];
+            else
+              t[q] = gz * C[2 * 6 + q] + gx * C[4 * 6 + q] + gy * C[5 * 6 + q];
+          }
+#pragma unroll
+          for (int jn = 0; jn < 8; ++jn) {
+            const double hx = P.dsh[gp][jn * 3 + 0], hy = P.dsh[gp][jn * 3 + 1], hz = P.dsh[gp][jn * 3 + 2];
+            R[fi * 24 + jn * 3 + 0] += t[0] * hx + t[3] * hy + t[4] * hz;
+            R[fi * 24 + jn * 3 + 1] += t[1] * hy + t[3] * hx + t[5] * hz;
+            R[fi * 24 + jn * 3 + 2] += t[2] * hz + t[4] * hx + t[5] * hy;
+          }
+        }
+      }
+    }
+  }
+
+  // add the eight row blocks in the reference's element order (c ascending == ex outermost)
+  for (int round = 0; round < 8; ++round) {
+    if (work && c == round) {
+      double *row = s_acc + ln * NPLANE;
+      const int cxa = corner_x(a), cya = corner_y(a), cza = corner_z(a);
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn) {
+        const int pl = nbr_slot(corner_x(jn) - cxa, corner_y(jn) - cya, corner_z(jn) - cza) * 9;
+#pragma unroll
+        for (int fi = 0; fi < 3; ++fi)
+#pragma unroll
+          for (int fj = 0; fj < 3; ++fj) row[pl + fi * 3 + fj] += R[fi * 24 + jn * 3 + fj];
+      }
+    }
+    __syncthreads();
+  }
+  if (valid && bnd && c == 0) {
+    double *row = s_acc + ln * NPLANE;
+    row[13 * 9 + 0] = 1.0;
+    row[13 * 9 + 4] = 1.0;
+    row[13 * 9 + 8] = 1.0;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < GN * NPLANE; q += NT) {
+    const int pl = q / GN, l = q % GN;
+    const int nd = blockIdx.x * GN + l;
+    if (nd < P.nn) A[(size_t)pl * P.nn_pad + nd] = s_acc[l * NPLANE + pl];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DPCG (src/ell.cpp:66-122)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+    k_cg_init(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V,
+              int use_shared) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  const double *A = use_shared ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double red[2] = {0.0, 0.0};
+  if (n < P.nn) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t ix = vo + (size_t)d * P.nn_pad + n;
+      const double diag = A[(size_t)(13 * 9 + d * 4) * P.nn_pad + n];
+      const double kk = 1 / diag;  // src/ell.cpp:73-76
+      const double r = V.b[ix];    // r = b - A*0 (src/ell.cpp:78-82)
+      const double z = kk * r;
+      V.k[ix] = kk;
+      V.du[ix] = 0.0;
+      V.r[ix] = r;
+      V.z[ix] = z;
+      V.p[ix] = z;
+      red[0] += r * z;
+      red[1] += z * z;
+    }
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    const double pn = sqrt(red[1]);
+    st->rz = red[0];
+    st->pnorm0 = pn;
+    st->pnorm = pn;
+    st->cg_its = 0;
+    // loop head of src/ell.cpp:93-94
+    st->cg_active = (0 < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < pn * P.cg_rel_tol);
+  }
+}
+
+// Ap = A p fused with p.Ap.  Thread per node: 3 rows, 243 coalesced value loads (one per plane),
+// 81 p loads that hit L1 (each p value is reused by 27 nodes x 3 rows).
+template <int NBR>
+__device__ __forceinline__ void spmv_slot(const double *__restrict__ A, const double *__restrict__ p, size_t npad,
+                                          int n, int nx, int nxny, double &y0, double &y1, double &y2) {
+  constexpr int DI = NBR % 3 - 1, DJ = (NBR / 3) % 3 - 1, DK = NBR / 9 - 1;
+  const int m = n + DI + DJ * nx + DK * nxny;
+  const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
+  const double *a = A + (size_t)(NBR * 9) * npad + n;
+  y0 += a[0] * px;
+  y0 += a[npad] * py;
+  y0 += a[2 * npad] * pz;
+  y1 += a[3 * npad] * px;
+  y1 += a[4 * npad] * py;
+  y1 += a[5 * npad] * pz;
+  y2 += a[6 * npad] * px;
+  y2 += a[7 * npad] * py;
+  y2 += a[8 * npad] * pz;
+}
+template <int NBR>
+struct SpmvLoop {
+  static __device__ __forceinline__ void run(const double *__restrict__ A, const double *__restrict__ p,
+                                             size_t npad, int n, int nx, int nxny, double &y0, double &y1,
+                                             double &y2) {
+    spmv_slot<NBR>(A, p, npad, n, nx, nxny, y0, y1, y2);
+    SpmvLoop<NBR + 1>::run(A, p, npad, n, nx, nxny, y0, y1, y2);
+  }
+};
+template <>
+struct SpmvLoop<27> {
+  static __device__ __forceinline__ void run(const double *__restrict__, const double *__restrict__, size_t, int,
+                                             int, int, double &, double &, double &) {}
+};
+
+// Generic row (any node, neighbours outside the grid skipped -- their stored value is 0 and the
+// reference multiplies it by x[fj], src/ell-common.cpp:102-130 + src/ell.cpp:39-41).
+__device__ __forceinline__ void spmv_row_checked(const MeshConst &P, const double *__restrict__ A,
+                                                 const double *__restrict__ p, int n, int i, int j, int k,
+                                                 double &y0, double &y1, double &y2) {
+  const size_t npad = P.nn_pad;
+  for (int nbr = 0; nbr < 27; ++nbr) {
+    const int di = nbr % 3 - 1, dj = (nbr / 3) % 3 - 1, dk = nbr / 9 - 1;
+    const int ii = i + di, jj = j + dj, kk = k + dk;
+    if (ii < 0 || ii >= P.nx || jj < 0 || jj >= P.ny || kk < 0 || kk >= P.nz) continue;
+    const int m = n + di + dj * P.nx + dk * P.nxny;
+    const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
+    const double *a = A + (size_t)(nbr * 9) * npad + n;
+    y0 += a[0] * px;
+    y0 += a[npad] * py;
+    y0 += a[2 * npad] * pz;
+    y1 += a[3 * npad] * px;
+    y1 += a[4 * npad] * py;
+    y1 += a[5 * npad] * pz;
+    y2 += a[6 * npad] * px;
+    y2 += a[7 * npad] * py;
+    y2 += a[8 * npad] * pz;
+  }
+}
+
+// GENERIC = false: Newton path, boundary rows are known identity rows (ell_set_bc_3D) => Ap = p there.
+// GENERIC = true : arbitrary user matrix (host-pointer ell_mvp / ell_solve_cgpd API).
+template <bool GENERIC>
+__global__ void __launch_bounds__(NT)
+    k_spmv_dot(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V,
+               int use_shared, int force) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  if (!force && !st->cg_active) return;
+  const double *A = use_shared ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
+  const size_t vo = (size_t)slot * V.vstride;
+  const double *p = V.p + vo;
+  double *Ap = V.Ap + vo;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double red[1] = {0.0};
+  if (n < P.nn) {
+    int i, j, k;
+    node_ijk(P, n, i, j, k);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    const size_t npad = P.nn_pad;
+    const double p0 = p[n], p1 = p[npad + n], p2 = p[2 * npad + n];
+    if (on_boundary(P, i, j, k)) {
+      if (GENERIC) {
+        spmv_row_checked(P, A, p, n, i, j, k, y0, y1, y2);
+      } else {
+        y0 = p0;
+        y1 = p1;
+        y2 = p2;
+      }
+    } else {
+      SpmvLoop<0>::run(A, p, npad, n, P.nx, P.nxny, y0, y1, y2);
+    }
+    Ap[n] = y0;
+    Ap[npad + n] = y1;
+    Ap[2 * npad + n] = y2;
+    red[0] = p0 * y0 + p1 * y1 + p2 * y2;
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<1>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    st->pAp = red[0];
+    st->alpha = st->rz / red[0];  // src/ell.cpp:100
+  }
+}
+
+// x += alpha p ; r -= alpha Ap ; z = k r ; z.z ; r.z   (src/ell.cpp:102-110), then the scalar tail
+// of the iteration and the loop-head test of the next one (src/ell.cpp:93-94,108-119).
+__global__ void __launch_bounds__(NT)
+    k_cg_update(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  if (!st->cg_active) return;
+  const double alpha = st->alpha;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double red[2] = {0.0, 0.0};
+  if (n < P.nn) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t ix = vo + (size_t)d * P.nn_pad + n;
+      const double pp = V.p[ix];
+      V.du[ix] += alpha * pp;
+      const double r = V.r[ix] - alpha * V.Ap[ix];
+      V.r[ix] = r;
+      const double z = V.k[ix] * r;
+      V.z[ix] = z;
+      red[0] += z * z;
+      red[1] += r * z;
+    }
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    const double pn = sqrt(red[0]);
+    const double rz_n = red[1];
+    st->pnorm = pn;
+    st->beta = rz_n / st->rz;
+    st->rz = rz_n;
+    const int its = ++st->cg_its;
+    st->cg_active = (its < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < st->pnorm0 * P.cg_rel_tol);
+  }
+}
+
+// p = z + beta p (src/ell.cpp:113); skipped once the slot has left the loop (p is dead then).
+__global__ void __launch_bounds__(NT)
+    k_cg_pupdate(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
+  const int slot = list[blockIdx.y];
+  const mgpu_slot_state *st = &T.state[slot];
+  if (!st->cg_active) return;
+  const double beta = st->beta;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= P.nn) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const size_t ix = vo + (size_t)d * P.nn_pad + n;
+    V.p[ix] = V.z[ix] + beta * V.p[ix];
+  }
+}
+
+// u += du (src/solve.cpp:73) and newton.solver_its += cg_its (src/solve.cpp:71)
+__global__ void __launch_bounds__(NT)
+    k_axpy_u(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  if (!st->nr_active) return;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->solver_its += st->cg_its;
+  if (n >= P.nn) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const size_t ix = vo + (size_t)d * P.nn_pad + n;
+    V.u[ix] += V.du[ix];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// calc_ave_stress (src/average.cpp:58-82): thread per element
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+    k_ave_stress(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+                 const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  const double *u = u_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  const int e = blockIdx.x * NT + threadIdx.x;
+  double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (e < P.nelem) {
+    const int ez = e / (P.nex * P.ney);
+    const int r = e - ez * P.nex * P.ney;
+    const int ey = r / P.nex, ex = r - ey * P.nex;
+    double ue[24];
+    gather_ue(P, u, ex, ey, ez, ue);
+    const int type = __ldg(&elem_type[e]);
+    const mpp_material m = P.mat[type];
+    const int nv = mat_nvar(m.type);
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+      double eps[6], sig[6], vbuf[7];
+      gp_strain(P.dsh[gp], ue, eps);
+      const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+      mat_stress(m, eps, v, sig);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) red[q] = add_(red[q], mul_(sig[q], P.wg));  // src/average.cpp:70-72, uncontracted
+    }
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<6>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) T.stress[slot * 6 + q] = red[q] / 1.0;  // vol_tot = 1 (src/micropp.cpp:58)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// calc_vars_new (src/update.cpp:33-56): thread per element; write = 0 only raises the non-linear flag
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+    k_vars_new(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+               const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type, int write) {
+  const int slot = list[blockIdx.y];
+  mgpu_slot_state *st = &T.state[slot];
+  const double *u = u_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  double *vnew = write ? T.vars_new[slot] : nullptr;
+  const int e = blockIdx.x * NT + threadIdx.x;
+  bool nl = false;
+  if (e < P.nelem) {
+    const int type = __ldg(&elem_type[e]);
+    const mpp_material m = P.mat[type];
+    if (m.type != MPP_ELASTIC) {
+      const int ez = e / (P.nex * P.ney);
+      const int r = e - ez * P.nex * P.ney;
+      const int ey = r / P.nex, ex = r - ey * P.nex;
+      double ue[24];
+      gather_ue(P, u, ex, ey, ez, ue);
+      const int nv = mat_nvar(m.type);
+#pragma unroll 1
+      for (int gp = 0; gp < 8; ++gp) {
+        double eps[6], vbuf[7], vn[7];
+        gp_strain(P.dsh[gp], ue, eps);
+        const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+        // plastic evolute writes nothing without an old state (src/material.cpp:180-183)
+        const bool wr = vnew && (m.type == MPP_DAMAGE || v != nullptr);
+        nl |= mat_evolute(m, eps, v, wr ? vn : nullptr);
+        if (wr)
+          for (int q = 0; q < nv; ++q) vnew[(size_t)(q * 8 + gp) * P.nelem_pad + e] = vn[q];
+      }
+    }
+  }
+  if (__syncthreads_or(nl) && threadIdx.x == 0) atomicOr(&st->nl_flag, 1);
+}
+
+__global__ void k_clear_nl(const int *__restrict__ list, int n, SlotTables T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) T.state[list[i]].nl_flag = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable compaction of a slot list by an activity flag (single block)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_compact(const int *in, int n_in, int *out, int *count, SlotTables T, int mode) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int start = 0; start < n_in; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    int slot = -1, keep = 0;
+    if (i < n_in) {
+      slot = in[i];
+      const mgpu_slot_state *st = &T.state[slot];
+      keep = mode ? st->cg_active : st->nr_active;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int ww = 0; ww < w; ++ww) off += s_warp[ww];
+    if (keep) out[off + __popc(bal & ((1u << lane) - 1u))] = slot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int ww = 0; ww < nw; ++ww) tot += s_warp[ww];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bit-exact regeneration of the reference's explicit ELL column table (src/ell-common.cpp:86-137):
+// the product never stores it (columns are implicit); this exporter exists for parity tests.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ell_cols(int nx, int ny, int nz, int *cols) {
+  const int nn = nx * ny * nz;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= 3 * nn) return;
+  const int n = row / 3;
+  const int k = n / (nx * ny), r = n - k * nx * ny, j = r / nx, i = r - j * nx;
+  for (int nbr = 0; nbr < 27; ++nbr) {
+    const int di = nbr % 3 - 1, dj = (nbr / 3) % 3 - 1, dk = nbr / 9 - 1;
+    const int ii = i + di, jj = j + dj, kk = k + dk;
+    const bool in = ii >= 0 && ii < nx && jj >= 0 && jj < ny && kk >= 0 && kk < nz;
+    const int m = in ? n + di + dj * nx + dk * nx * ny : 0;  // out-of-grid neighbours point at node 0
+    for (int fj = 0; fj < 3; ++fj) cols[(size_t)row * 81 + nbr * 3 + fj] = m * 3 + fj;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// host side of the thin layer
+// ================================================================================================
+struct mgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  MeshConst mc;
+  int ngp = 0, W = 0;
+  bool all_elastic = true;
+  int *d_elem_type = nullptr;
+  double *d_ke = nullptr;
+  VecPool V{};
+  SlotTables T{};
+  int *d_list[NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int *d_count = nullptr;
+  int *h_count = nullptr;  // pinned
+  // persistent per-GP state
+  double *d_ustore = nullptr;  // [ngp][2][3*nn_pad]
+  std::vector<double *> u_n, u_k, vars_n, vars_k;
+  std::vector<double *> var_chunks;
+  std::vector<double *> var_free;
+  size_t var_len = 0;  // doubles per vars buffer
+  // slot tables (host mirrors)
+  std::vector<int> slot_gp;
+  std::vector<const double *> h_vars_old;
+  std::vector<double *> h_vars_new, h_un, h_uk;
+  // staging buffers for the host-pointer API
+  std::vector<double *> stage_vars[2];
+  // measurement
+  bool prof = false;
+  struct EvPair {
+    cudaEvent_t a, b;
+    int kind;
+    int slots;
+  };
+  std::vector<EvPair> ev_live, ev_pool;
+  double prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  unsigned long long launches = 0;
+};
+
+namespace {
+
+inline dim3 node_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT - 1) / NT, n, 1); }
+inline dim3 elem_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nelem + NT - 1) / NT, n, 1); }
+
+struct ProfScope {
+  mgpu_ctx *c;
+  int kind, slots;
+  bool on;
+  mgpu_ctx::EvPair ev;
+  ProfScope(mgpu_ctx *c_, int kind_, int slots_) : c(c_), kind(kind_), slots(slots_), on(c_->prof) {
+    c->launches++;
+    if (!on) return;
+    if (c->ev_pool.empty()) {
+      CK(cudaEventCreate(&ev.a));
+      CK(cudaEventCreate(&ev.b));
+    } else {
+      ev = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    }
+    ev.kind = kind;
+    ev.slots = slots;
+    CK(cudaEventRecord(ev.a, c->stream));
+  }
+  ~ProfScope() {
+    if (!on) return;
+    CK(cudaEventRecord(ev.b, c->stream));
+    c->ev_live.push_back(ev);
+  }
+};
+
+void prof_drain(mgpu_ctx *c) {
+  if (c->ev_live.empty()) return;
+  CK(cudaStreamSynchronize(c->stream));
+  for (auto &e : c->ev_live) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e.a, e.b));
+    switch (e.kind) {
+      case 0:
+        c->prof_acc[0] += ms;
+        c->prof_acc[1] += 1;
+        c->prof_acc[2] += e.slots;
+        break;
+      case 1: c->prof_acc[3] += ms; break;
+      case 2: c->prof_acc[4] += ms; break;
+      case 3: c->prof_acc[5] += ms; break;
+      default: break;
+    }
+    c->ev_pool.push_back(e);
+  }
+  c->ev_live.clear();
+}
+
+void upload_slot_tables(mgpu_ctx *c) {
+  const size_t W = c->W;
+  CK(cudaMemcpyAsync((void *)c->T.vars_old, c->h_vars_old.data(), W * sizeof(double *), cudaMemcpyHostToDevice,
+                     c->stream));
+  CK(cudaMemcpyAsync((void *)c->T.vars_new, c->h_vars_new.data(), W * sizeof(double *), cudaMemcpyHostToDevice,
+                     c->stream));
+  CK(cudaMemcpyAsync((void *)c->T.u_n, c->h_un.data(), W * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync((void *)c->T.u_k, c->h_uk.data(), W * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+}
+
+double *vars_buffer_alloc(mgpu_ctx *c) {
+  if (c->var_free.empty()) {
+    // grow the pool by a chunk of buffers (never returned to the driver before mgpu_destroy)
+    const size_t per = c->var_len;
+    size_t nbuf = std::max<size_t>(2, std::min<size_t>(64, (size_t(1) << 30) / (per * sizeof(double) + 1)));
+    double *chunk = nullptr;
+    CK(cudaMalloc(&chunk, nbuf * per * sizeof(double)));
+    c->var_chunks.push_back(chunk);
+    for (size_t i = 0; i < nbuf; ++i) c->var_free.push_back(chunk + i * per);
+  }
+  double *p = c->var_free.back();
+  c->var_free.pop_back();
+  CK(cudaMemsetAsync(p, 0, c->var_len * sizeof(double), c->stream));
+  return p;
+}
+
+// reference AoS [e][gp][7] (include/params.hpp:41) <-> internal [(v*8+gp)*nelem_pad + e]
+void vars_ref_to_internal(const mgpu_ctx *c, const double *ref, std::vector<double> &out) {
+  const int nelem = c->mc.nelem, npad = c->mc.nelem_pad, nv = c->mc.nvar;
+  out.assign((size_t)nv * 8 * npad, 0.0);
+  for (int e = 0; e < nelem; ++e)
+    for (int gp = 0; gp < 8; ++gp)
+      for (int v = 0; v < nv; ++v) out[(size_t)(v * 8 + gp) * npad + e] = ref[(size_t)e * 56 + gp * 7 + v];
+}
+void vars_internal_to_ref(const mgpu_ctx *c, const std::vector<double> &in, double *ref) {
+  const int nelem = c->mc.nelem, npad = c->mc.nelem_pad, nv = c->mc.nvar;
+  memset(ref, 0, sizeof(double) * (size_t)nelem * 56);
+  for (int e = 0; e < nelem; ++e)
+    for (int gp = 0; gp < 8; ++gp)
+      for (int v = 0; v < nv; ++v) ref[(size_t)e * 56 + gp * 7 + v] = in[(size_t)(v * 8 + gp) * npad + e];
+}
+void aos_to_soa(const mgpu_ctx *c, const double *aos, std::vector<double> &soa) {
+  const int nn = c->mc.nn, npad = c->mc.nn_pad;
+  soa.assign((size_t)3 * npad, 0.0);
+  for (int n = 0; n < nn; ++n)
+    for (int d = 0; d < 3; ++d) soa[(size_t)d * npad + n] = aos[(size_t)n * 3 + d];
+}
+void soa_to_aos(const mgpu_ctx *c, const std::vector<double> &soa, double *aos) {
+  const int nn = c->mc.nn, npad = c->mc.nn_pad;
+  for (int n = 0; n < nn; ++n)
+    for (int d = 0; d < 3; ++d) aos[(size_t)n * 3 + d] = soa[(size_t)d * npad + n];
+}
+
+double *vec_of(mgpu_ctx *c, int which) {
+  switch (which) {
+    case 0: return c->V.b;
+    case 1: return c->V.du;
+    case 2: return c->V.Ap;
+    case 3: return c->V.p;
+    case 4: return c->V.u;
+    default: return c->V.r;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    // No CPU fallback by design: the hot path exists only as sm_100a kernels.
+    fprintf(stderr, "micropp-b200: no CUDA device available (%s); this library has no CPU path\n",
+            cudaGetErrorString(err));
+    abort();
+  }
+  mgpu_ctx *c = new mgpu_ctx();
+  c->device = cfg->device % ndev;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->t0));
+  CK(cudaEventCreate(&c->t1));
+
+  MeshConst &P = c->mc;
+  memset(&P, 0, sizeof(P));
+  P.nx = cfg->nx;
+  P.ny = cfg->ny;
+  P.nz = cfg->nz;
+  P.nxny = P.nx * P.ny;
+  P.nn = P.nx * P.ny * P.nz;
+  P.nn_pad = (P.nn + 31) / 32 * 32;
+  P.nex = P.nx - 1;
+  P.ney = P.ny - 1;
+  P.nez = P.nz - 1;
+  P.nelem = P.nex * P.ney * P.nez;
+  P.nelem_pad = (P.nelem + 31) / 32 * 32;
+  P.nr_max_its = cfg->nr_max_its;
+  P.cg_max_its = cfg->cg_max_its;
+  P.dx = cfg->dx;
+  P.dy = cfg->dy;
+  P.dz = cfg->dz;
+  P.wg = cfg->wg;
+  P.nr_max_tol = cfg->nr_max_tol;
+  P.nr_rel_tol = cfg->nr_rel_tol;
+  P.cg_abs_tol = cfg->cg_abs_tol;
+  P.cg_rel_tol = cfg->cg_rel_tol;
+  memcpy(P.dsh, cfg->dsh, sizeof(P.dsh));
+  int nvar = 0;
+  c->all_elastic = true;
+  for (int i = 0; i < 3; ++i) {
+    mpp_material &m = P.mat[i];
+    m.E = cfg->mat[i][0];
+    m.nu = cfg->mat[i][1];
+    m.Ka = cfg->mat[i][2];
+    m.Sy = cfg->mat[i][3];
+    m.k = cfg->mat[i][4];
+    m.mu = cfg->mat[i][5];
+    m.lambda = cfg->mat[i][6];
+    m.Xt = cfg->mat[i][7];
+    m.type = cfg->mat_type[i];
+  }
+  // only materials that actually occur in the micro-structure count
+  bool used[3] = {false, false, false};
+  for (int e = 0; e < P.nelem; ++e) {
+    const int t = cfg->elem_type[e];
+    if (t < 0 || t > 2) {
+      fprintf(stderr, "micropp-b200: invalid element type %d\n", t);
+      abort();
+    }
+    used[t] = true;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (used[i]) {
+      nvar = std::max(nvar, mat_nvar(P.mat[i].type));
+      if (P.mat[i].type != MPP_ELASTIC) c->all_elastic = false;
+    }
+  P.nvar = nvar;
+  c->var_len = (size_t)std::max(nvar, 1) * 8 * P.nelem_pad;
+  c->ngp = cfg->ngp;
+
+  CK(cudaMalloc(&c->d_elem_type, sizeof(int) * std::max(P.nelem, 1)));
+  CK(cudaMemcpy(c->d_elem_type, cfg->elem_type, sizeof(int) * P.nelem, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_ke, sizeof(double) * 3 * 576));
+  CK(cudaMemcpy(c->d_ke, cfg->ke_elastic, sizeof(double) * 3 * 576, cudaMemcpyHostToDevice));
+
+  // persistent displacement state u_n,u_k of every FE Gauss point
+  const size_t vlen = (size_t)3 * P.nn_pad;
+  const int ngp = std::max(cfg->ngp, 0);
+  if (ngp > 0) {
+    CK(cudaMalloc(&c->d_ustore, sizeof(double) * vlen * 2 * ngp));
+    CK(cudaMemset(c->d_ustore, 0, sizeof(double) * vlen * 2 * ngp));
+  }
+  c->u_n.resize(ngp);
+  c->u_k.resize(ngp);
+  c->vars_n.assign(ngp, nullptr);
+  c->vars_k.assign(ngp, nullptr);
+  for (int g = 0; g < ngp; ++g) {
+    c->u_n[g] = c->d_ustore + (size_t)g * 2 * vlen;
+    c->u_k[g] = c->u_n[g] + vlen;
+  }
+
+  // wave size from the HBM left after reserving room for internal variables of every GP
+  const size_t mlen = (size_t)NPLANE * P.nn_pad;
+  const int nblk_max = std::max((P.nn + NT - 1) / NT, (P.nelem + NT - 1) / NT);
+  const size_t per_slot = sizeof(double) * (mlen + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  size_t reserve = sizeof(double) * mlen /* A0 */ + (size_t(1) << 30);
+  if (!c->all_elastic) reserve += (size_t)ngp * 2 * c->var_len * sizeof(double);
+  size_t avail = free_b > reserve ? free_b - reserve : 0;
+  avail = (size_t)(avail * 0.92);
+  long long W = (long long)(avail / per_slot);
+  const int want = std::max(ngp, 6);  // at least the 6 unit-strain solves of calc_ctan_lin_fe_models
+  if (W > want) W = want;
+  if (cfg->wave_cap > 0 && W > cfg->wave_cap) W = cfg->wave_cap;
+  if (const char *env = getenv("MICROPP_WAVE")) {
+    const long long w = atoll(env);
+    if (w > 0 && W > w) W = w;
+  }
+  if (W < 1) {
+    fprintf(stderr, "micropp-b200: not enough device memory for one %dx%dx%d RVE\n", P.nx, P.ny, P.nz);
+    abort();
+  }
+  c->W = (int)W;
+
+  VecPool &V = c->V;
+  V.vstride = vlen;
+  V.mstride = mlen;
+  double **vecs[8] = {&V.u, &V.b, &V.du, &V.k, &V.r, &V.z, &V.p, &V.Ap};
+  for (auto pp : vecs) {
+    CK(cudaMalloc(pp, sizeof(double) * vlen * W));
+    CK(cudaMemset(*pp, 0, sizeof(double) * vlen * W));
+  }
+  CK(cudaMalloc(&V.mat, sizeof(double) * mlen * W));
+  V.mat_shared = nullptr;  // allocated on first use (use_A0)
+
+  SlotTables &T = c->T;
+  T.nblk_max = nblk_max;
+  CK(cudaMalloc(&T.state, sizeof(mgpu_slot_state) * W));
+  CK(cudaMemset(T.state, 0, sizeof(mgpu_slot_state) * W));
+  CK(cudaMalloc((void **)&T.vars_old, sizeof(double *) * W));
+  CK(cudaMalloc((void **)&T.vars_new, sizeof(double *) * W));
+  CK(cudaMalloc((void **)&T.u_n, sizeof(double *) * W));
+  CK(cudaMalloc((void **)&T.u_k, sizeof(double *) * W));
+  CK(cudaMalloc(&T.eps, sizeof(double) * 6 * W));
+  CK(cudaMalloc(&T.stress, sizeof(double) * 6 * W));
+  CK(cudaMemset(T.eps, 0, sizeof(double) * 6 * W));
+  CK(cudaMemset(T.stress, 0, sizeof(double) * 6 * W));
+  CK(cudaMalloc(&T.partial, sizeof(double) * (size_t)NRED * nblk_max * W));
+  for (int l = 0; l < NLIST; ++l) CK(cudaMalloc(&c->d_list[l], sizeof(int) * W));
+  CK(cudaMalloc(&c->d_count, sizeof(int)));
+  CK(cudaMallocHost(&c->h_count, sizeof(int)));
+
+  c->slot_gp.assign(W, -1);
+  c->h_vars_old.assign(W, nullptr);
+  c->h_vars_new.assign(W, nullptr);
+  c->h_un.assign(W, nullptr);
+  c->h_uk.assign(W, nullptr);
+  upload_slot_tables(c);
+
+  CK(cudaFuncSetAttribute(k_asm_mat_general, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)(GN * NPLANE * sizeof(double))));
+  CK(cudaStreamSynchronize(c->stream));
+  return c;
+}
+
+void mgpu_destroy(mgpu_ctx *c) {
+  if (!c) return;
+  CK(cudaSetDevice(c->device));
+  cudaStreamSynchronize(c->stream);
+  prof_drain(c);
+  for (auto &e : c->ev_pool) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  double *vecs[9] = {c->V.u, c->V.b, c->V.du, c->V.k, c->V.r, c->V.z, c->V.p, c->V.Ap, c->V.mat};
+  for (auto p : vecs) cudaFree(p);
+  if (c->V.mat_shared) cudaFree(c->V.mat_shared);
+  cudaFree(c->T.state);
+  cudaFree((void *)c->T.vars_old);
+  cudaFree((void *)c->T.vars_new);
+  cudaFree((void *)c->T.u_n);
+  cudaFree((void *)c->T.u_k);
+  cudaFree(c->T.eps);
+  cudaFree(c->T.stress);
+  cudaFree(c->T.partial);
+  for (int l = 0; l < NLIST; ++l) cudaFree(c->d_list[l]);
+  cudaFree(c->d_count);
+  cudaFreeHost(c->h_count);
+  cudaFree(c->d_elem_type);
+  cudaFree(c->d_ke);
+  if (c->d_ustore) cudaFree(c->d_ustore);
+  for (auto p : c->var_chunks) cudaFree(p);
+  for (int w = 0; w < 2; ++w)
+    for (auto p : c->stage_vars[w])
+      if (p) cudaFree(p);
+  cudaEventDestroy(c->t0);
+  cudaEventDestroy(c->t1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mgpu_wave_size(const mgpu_ctx *c) { return c->W; }
+int mgpu_nn_pad(const mgpu_ctx *c) { return c->mc.nn_pad; }
+int mgpu_nelem_pad(const mgpu_ctx *c) { return c->mc.nelem_pad; }
+int mgpu_nvar(const mgpu_ctx *c) { return c->mc.nvar; }
+void mgpu_sync(mgpu_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+}
+unsigned long long mgpu_launch_count(const mgpu_ctx *c) { return c->launches; }
+
+// ---- per-GP persistent state ---------------------------------------------------------------
+void mgpu_gp_swap(mgpu_ctx *c, int gp) {
+  std::swap(c->u_n[gp], c->u_k[gp]);
+  std::swap(c->vars_n[gp], c->vars_k[gp]);
+}
+int mgpu_gp_has_vars(const mgpu_ctx *c, int gp) { return c->vars_n[gp] != nullptr; }
+void mgpu_gp_alloc_vars(mgpu_ctx *c, int gp) {
+  CK(cudaSetDevice(c->device));
+  if (c->vars_n[gp]) return;
+  c->vars_n[gp] = vars_buffer_alloc(c);
+  c->vars_k[gp] = vars_buffer_alloc(c);
+}
+void mgpu_gp_get_u(mgpu_ctx *c, int gp, int which, double *host_aos) {
+  CK(cudaSetDevice(c->device));
+  std::vector<double> tmp((size_t)3 * c->mc.nn_pad);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(tmp.data(), which ? c->u_k[gp] : c->u_n[gp], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  soa_to_aos(c, tmp, host_aos);
+}
+void mgpu_gp_set_u(mgpu_ctx *c, int gp, int which, const double *host_aos) {
+  CK(cudaSetDevice(c->device));
+  std::vector<double> tmp;
+  aos_to_soa(c, host_aos, tmp);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(which ? c->u_k[gp] : c->u_n[gp], tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+void mgpu_gp_get_vars(mgpu_ctx *c, int gp, int which, double *ref) {
+  CK(cudaSetDevice(c->device));
+  const double *src = which ? c->vars_k[gp] : c->vars_n[gp];
+  if (!src) {
+    memset(ref, 0, sizeof(double) * (size_t)c->mc.nelem * 56);
+    return;
+  }
+  std::vector<double> tmp(c->var_len);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  vars_internal_to_ref(c, tmp, ref);
+}
+void mgpu_gp_set_vars(mgpu_ctx *c, int gp, int which, const double *ref) {
+  CK(cudaSetDevice(c->device));
+  mgpu_gp_alloc_vars(c, gp);
+  std::vector<double> tmp;
+  vars_ref_to_internal(c, ref, tmp);
+  tmp.resize(c->var_len, 0.0);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(which ? c->vars_k[gp] : c->vars_n[gp], tmp.data(), tmp.size() * sizeof(double),
+                cudaMemcpyHostToDevice));
+}
+
+// ---- wave set-up ----------------------------------------------------------------------------
+void mgpu_bind_slots(mgpu_ctx *c, int n, const int *slots, const int *gps, const int *use_vars_old) {
+  CK(cudaSetDevice(c->device));
+  for (int i = 0; i < n; ++i) {
+    const int s = slots[i], g = gps[i];
+    c->slot_gp[s] = g;
+    if (g >= 0) {
+      c->h_un[s] = c->u_n[g];
+      c->h_uk[s] = c->u_k[g];
+      c->h_vars_old[s] = (use_vars_old && use_vars_old[i]) ? c->vars_n[g] : nullptr;
+      c->h_vars_new[s] = c->vars_k[g];
+    } else {
+      c->h_un[s] = c->h_uk[s] = nullptr;
+      c->h_vars_old[s] = nullptr;
+      c->h_vars_new[s] = nullptr;
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));  // the pageable host mirrors are re-used across calls
+  upload_slot_tables(c);
+  CK(cudaStreamSynchronize(c->stream));
+}
+
+void mgpu_set_slot_strain(mgpu_ctx *c, int n, const int *slots, const double *eps6) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  // contiguous runs are the common case; fall back to per-slot copies otherwise
+  bool contiguous = true;
+  for (int i = 1; i < n; ++i) contiguous &= (slots[i] == slots[0] + i);
+  if (contiguous && n > 0) {
+    CK(cudaMemcpy(c->T.eps + (size_t)slots[0] * 6, eps6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice));
+  } else {
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy(c->T.eps + (size_t)slots[i] * 6, eps6 + (size_t)i * 6, sizeof(double) * 6,
+                    cudaMemcpyHostToDevice));
+  }
+}
+
+void mgpu_set_list(mgpu_ctx *c, int which_list, int n, const int *slots) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(c->d_list[which_list], slots, sizeof(int) * n, cudaMemcpyHostToDevice));
+}
+
+// ---- kernels --------------------------------------------------------------------------------
+void mgpu_load_u(mgpu_ctx *c, int l, int n, int which_u) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  const int len = 3 * c->mc.nn_pad;
+  dim3 g(std::min((len + 255) / 256, 1024), n);
+  k_load_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, which_u);
+  CK(cudaGetLastError());
+}
+void mgpu_store_u(mgpu_ctx *c, int l, int n, int which_u) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  const int len = 3 * c->mc.nn_pad;
+  dim3 g(std::min((len + 255) / 256, 1024), n);
+  k_store_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, which_u);
+  CK(cudaGetLastError());
+}
+void mgpu_zero_u(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  const int len = 3 * c->mc.nn_pad;
+  dim3 g(std::min((len + 255) / 256, 1024), n);
+  k_zero_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->V.u, c->V.vstride);
+  CK(cudaGetLastError());
+}
+void mgpu_set_bc(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  k_set_bc<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride);
+  CK(cudaGetLastError());
+}
+void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
+  if (n <= 0) return;
+  ProfScope ps(c, 2, n);
+  k_asm_rhs<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.b, c->V.vstride,
+                                                  c->d_elem_type, mode);
+  CK(cudaGetLastError());
+}
+void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
+  if (n <= 0) return;
+  double *shared = nullptr;
+  if (to_shared) {
+    if (!c->V.mat_shared) CK(cudaMalloc(&c->V.mat_shared, sizeof(double) * c->V.mstride));
+    shared = c->V.mat_shared;
+    n = 1;
+  }
+  ProfScope ps(c, 1, n);
+  if (c->all_elastic) {
+    k_asm_mat_elastic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->V.mat, c->V.mstride, shared,
+                                                            c->d_elem_type, c->d_ke);
+  } else {
+    dim3 g((c->mc.nn + GN - 1) / GN, n);
+    k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
+        c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke);
+  }
+  CK(cudaGetLastError());
+}
+void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
+  if (n <= 0) return;
+  ProfScope ps(c, 3, n);
+  k_cg_init<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, use_shared);
+  CK(cudaGetLastError());
+}
+void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
+  if (n <= 0) return;
+  ProfScope ps(c, 0, n);
+  k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, use_shared, 0);
+  CK(cudaGetLastError());
+}
+void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 3, n);
+  k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  CK(cudaGetLastError());
+}
+void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 3, n);
+  k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  CK(cudaGetLastError());
+}
+void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  CK(cudaGetLastError());
+}
+void mgpu_ave_stress(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  k_ave_stress<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride,
+                                                     c->d_elem_type);
+  CK(cudaGetLastError());
+}
+void mgpu_vars_new(mgpu_ctx *c, int l, int n, int write) {
+  if (n <= 0) return;
+  ProfScope ps(c, 9, n);
+  k_vars_new<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride,
+                                                   c->d_elem_type, write);
+  CK(cudaGetLastError());
+}
+void mgpu_clear_nl_flags(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  c->launches++;
+  k_clear_nl<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_list[l], n, c->T);
+  CK(cudaGetLastError());
+}
+int mgpu_compact(mgpu_ctx *c, int list_in, int n_in, int list_out, int mode) {
+  if (n_in <= 0) return 0;
+  c->launches++;
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in], n_in, c->d_list[list_out], c->d_count, c->T, mode);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return *c->h_count;
+}
+
+// ---- results ----------------------------------------------------------------------------------
+void mgpu_fetch_state(mgpu_ctx *c, int n, const int *slots, mgpu_slot_state *out) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  bool contiguous = true;
+  for (int i = 1; i < n; ++i) contiguous &= (slots[i] == slots[0] + i);
+  if (contiguous && n > 0) {
+    CK(cudaMemcpy(out, c->T.state + slots[0], sizeof(mgpu_slot_state) * n, cudaMemcpyDeviceToHost));
+  } else {
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy(out + i, c->T.state + slots[i], sizeof(mgpu_slot_state), cudaMemcpyDeviceToHost));
+  }
+}
+void mgpu_fetch_stress(mgpu_ctx *c, int n, const int *slots, double *sig6) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  bool contiguous = true;
+  for (int i = 1; i < n; ++i) contiguous &= (slots[i] == slots[0] + i);
+  if (contiguous && n > 0) {
+    CK(cudaMemcpy(sig6, c->T.stress + (size_t)slots[0] * 6, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
+  } else {
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy(sig6 + (size_t)i * 6, c->T.stress + (size_t)slots[i] * 6, sizeof(double) * 6,
+                    cudaMemcpyDeviceToHost));
+  }
+}
+
+// ---- staging ------------------------------------------------------------------------------------
+void mgpu_stage_put_vec(mgpu_ctx *c, int slot, int which, const double *host_aos) {
+  CK(cudaSetDevice(c->device));
+  std::vector<double> tmp;
+  aos_to_soa(c, host_aos, tmp);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(vec_of(c, which) + (size_t)slot * c->V.vstride, tmp.data(), tmp.size() * sizeof(double),
+                cudaMemcpyHostToDevice));
+}
+void mgpu_stage_get_vec(mgpu_ctx *c, int slot, int which, double *host_aos) {
+  CK(cudaSetDevice(c->device));
+  std::vector<double> tmp((size_t)3 * c->mc.nn_pad);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(tmp.data(), vec_of(c, which) + (size_t)slot * c->V.vstride, tmp.size() * sizeof(double),
+                cudaMemcpyDeviceToHost));
+  soa_to_aos(c, tmp, host_aos);
+}
+void mgpu_stage_put_u(mgpu_ctx *c, int slot, const double *host_aos) { mgpu_stage_put_vec(c, slot, 4, host_aos); }
+void mgpu_stage_get_u(mgpu_ctx *c, int slot, double *host_aos) { mgpu_stage_get_vec(c, slot, 4, host_aos); }
+
+void mgpu_stage_put_vars(mgpu_ctx *c, int slot, int which, const double *ref) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  auto &bufs = c->stage_vars[which];
+  if ((int)bufs.size() < c->W) bufs.resize(c->W, nullptr);
+  if (ref) {
+    if (!bufs[slot]) CK(cudaMalloc(&bufs[slot], sizeof(double) * c->var_len));
+    std::vector<double> tmp;
+    vars_ref_to_internal(c, ref, tmp);
+    tmp.resize(c->var_len, 0.0);
+    CK(cudaMemcpy(bufs[slot], tmp.data(), sizeof(double) * c->var_len, cudaMemcpyHostToDevice));
+  }
+  if (which == 0)
+    c->h_vars_old[slot] = ref ? bufs[slot] : nullptr;
+  else
+    c->h_vars_new[slot] = ref ? bufs[slot] : nullptr;
+  upload_slot_tables(c);
+  CK(cudaStreamSynchronize(c->stream));
+}
+void mgpu_stage_get_vars_new(mgpu_ctx *c, int slot, double *ref) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<double> tmp(c->var_len, 0.0);
+  if (c->h_vars_new[slot])
+    CK(cudaMemcpy(tmp.data(), c->h_vars_new[slot], sizeof(double) * c->var_len, cudaMemcpyDeviceToHost));
+  vars_internal_to_ref(c, tmp, ref);
+}
+void mgpu_stage_get_mat(mgpu_ctx *c, int slot, double *vals) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int nn = c->mc.nn, npad = c->mc.nn_pad;
+  std::vector<double> tmp(c->V.mstride);
+  CK(cudaMemcpy(tmp.data(), c->V.mat + (size_t)slot * c->V.mstride, sizeof(double) * c->V.mstride,
+                cudaMemcpyDeviceToHost));
+  // reference layout: vals[(3n+fi)*81 + nbr*3 + fj]
+  for (int n = 0; n < nn; ++n)
+    for (int nbr = 0; nbr < 27; ++nbr)
+      for (int fi = 0; fi < 3; ++fi)
+        for (int fj = 0; fj < 3; ++fj)
+          vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] = tmp[(size_t)(nbr * 9 + fi * 3 + fj) * npad + n];
+}
+void mgpu_stage_put_mat(mgpu_ctx *c, int slot, const double *vals) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int nn = c->mc.nn, npad = c->mc.nn_pad;
+  std::vector<double> tmp(c->V.mstride, 0.0);
+  for (int n = 0; n < nn; ++n)
+    for (int nbr = 0; nbr < 27; ++nbr)
+      for (int fi = 0; fi < 3; ++fi)
+        for (int fj = 0; fj < 3; ++fj)
+          tmp[(size_t)(nbr * 9 + fi * 3 + fj) * npad + n] = vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj];
+  CK(cudaMemcpy(c->V.mat + (size_t)slot * c->V.mstride, tmp.data(), sizeof(double) * c->V.mstride,
+                cudaMemcpyHostToDevice));
+}
+
+void mgpu_ell_cols(int nx, int ny, int nz, int *cols, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "micropp-b200: no CUDA device available; this library has no CPU path\n");
+    abort();
+  }
+  CK(cudaSetDevice(device % ndev));
+  const size_t nrow = (size_t)3 * nx * ny * nz;
+  int *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(int) * nrow * 81));
+  k_ell_cols<<<(unsigned)((nrow + 127) / 128), 128>>>(nx, ny, nz, d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(cols, d, sizeof(int) * nrow * 81, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+}
+
+// generic-matrix SpMV / CG steps for the host-pointer ELL API (arbitrary vals, no identity shortcut)
+void mgpu_spmv_generic(mgpu_ctx *c, int l, int n, int force) {
+  if (n <= 0) return;
+  ProfScope ps(c, 0, n);
+  k_spmv_dot<true><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, 0, force);
+  CK(cudaGetLastError());
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+void mgpu_prof_enable(mgpu_ctx *c, int on) {
+  prof_drain(c);
+  c->prof = on != 0;
+}
+void mgpu_prof_read(mgpu_ctx *c, double *out6, int reset) {
+  prof_drain(c);
+  for (int i = 0; i < 6; ++i) out6[i] = c->prof_acc[i];
+  if (reset)
+    for (int i = 0; i < 6; ++i) c->prof_acc[i] = 0;
+}
+void mgpu_timer_start(mgpu_ctx *c) { CK(cudaEventRecord(c->t0, c->stream)); }
+float mgpu_timer_stop(mgpu_ctx *c) {
+  CK(cudaEventRecord(c->t1, c->stream));
+  CK(cudaEventSynchronize(c->t1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->t0, c->t1));
+  return ms;
+}
+float mgpu_bench_spmv(mgpu_ctx *c, int n, int iters) {
+  CK(cudaSetDevice(c->device));
+  n = std::min(n, c->W);
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) ids[i] = i;
+  mgpu_set_list(c, 5, n, ids.data());
+  for (int w = 0; w < 2; ++w) {
+    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[5], c->T, c->V, 0, 1);
+  }
+  CK(cudaEventRecord(c->t0, c->stream));
+  for (int it = 0; it < iters; ++it) {
+    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[5], c->T, c->V, 0, 1);
+  }
+  CK(cudaEventRecord(c->t1, c->stream));
+  CK(cudaEventSynchronize(c->t1));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->t0, c->t1));
+  c->launches += iters + 2;
+  return ms / iters;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// mpp_engine.hpp -- internal: the batched Newton-Raphson / DPCG drivers shared by micropp_host.cpp and
+// ell_host.cpp.  Host C++ that only enqueues work through the thin C-ABI of include/mgpu.h.
+#pragma once
+
+#include <algorithm>
+#include <vector>
+
+#include "mgpu.h"
+#include "types.hpp"
+
+struct mpp_engine {
+  mgpu_ctx *ctx = nullptr;
+  int W = 0;
+  bool use_A0 = false;
+  int its_with_A0 = 1;
+  bool A0_ready = false;
+  int cg_chunk = 8;
+
+  // device slot lists: 0 = caller's list, 1 = Newton-active, 2/4 = CG-active (ping-pong), 3 = caller's subset
+  enum { L_OUTER = 0, L_NEWTON = 1, L_CG_A = 2, L_SUB = 3, L_CG_B = 4 };
+
+  // DPCG on the slots of `list` (src/ell.cpp:66-122).  The loop condition is evaluated on the device
+  // per slot; the host only learns how many slots are still iterating, every cg_chunk iterations.
+  void cg_solve(int list, int n, int use_shared, bool generic = false) {
+    mgpu_cg_init(ctx, list, n, use_shared);
+    int cur = L_CG_A, other = L_CG_B;
+    int nc = mgpu_compact(ctx, list, n, cur, 1);
+    while (nc > 0) {
+      for (int k = 0; k < cg_chunk; ++k) {
+        if (generic)
+          mgpu_spmv_generic(ctx, cur, nc, 0);
+        else
+          mgpu_cg_spmv_dot(ctx, cur, nc, use_shared);
+        mgpu_cg_update(ctx, cur, nc);
+        mgpu_cg_pupdate(ctx, cur, nc);
+      }
+      nc = mgpu_compact(ctx, cur, nc, other, 1);
+      std::swap(cur, other);
+    }
+  }
+
+  // Newton-Raphson on the slots of `list` (src/solve.cpp:29-82); u and the strain of every slot must
+  // already be in place.  All slots advance together; a slot that converged (or exhausted
+  // nr_max_its) simply drops out of the active list.
+  void newton_batch(int list, int n, const int *slots, std::vector<newton_t> &out) {
+    mgpu_set_bc(ctx, list, n);
+    mgpu_asm_rhs(ctx, list, n, 0);
+    int it = 0;
+    for (;;) {
+      const int na = mgpu_compact(ctx, list, n, L_NEWTON, 0);
+      if (na == 0) break;
+      int shared = 0;
+      if (use_A0 && A0_ready && it <= its_with_A0 - 1) {
+        shared = 1;  // linear Jacobian for the first its_with_A0 iterations (src/solve.cpp:56-66)
+      } else {
+        mgpu_asm_mat(ctx, L_NEWTON, na, 0);
+      }
+      cg_solve(L_NEWTON, na, shared);
+      mgpu_axpy_u(ctx, L_NEWTON, na);
+      mgpu_asm_rhs(ctx, L_NEWTON, na, 1);
+      ++it;
+    }
+    std::vector<mgpu_slot_state> st(n);
+    mgpu_fetch_state(ctx, n, slots, st.data());
+    out.resize(n);
+    for (int i = 0; i < n; ++i) {
+      out[i].its = st[i].nr_its;
+      out[i].solver_its = st[i].solver_its;
+      out[i].converged = st[i].converged != 0;
+    }
+  }
+};
+
