@@ -9,6 +9,7 @@ constructing a solver aborts if no CUDA device is visible.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -71,7 +72,7 @@ def load():
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first "
                            f"(`python -m micropp_b200.build`); micropp_b200 has no CPU fallback")
-    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL)  # keep micropp<3> symbols apart from any reference build in-process
     H = C.POINTER(Micropp3Handle)
     sig = {
         "micropp3_new": (None, [H, C.c_int, _ip, C.c_int, _dp, C.POINTER(MaterialBase), _ip, C.c_int, C.c_int]),

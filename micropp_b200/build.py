@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out:
             print(out)
     link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
-            "-cudart", "static"]
+            "-cudart", "static", "-Xlinker", "-Bsymbolic"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

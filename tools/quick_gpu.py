@@ -6,7 +6,8 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import micropp_b200 as M
-from tests.common import CASES
+sys.path.insert(0, "tests")
+from common import CASES
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 ngp = int(sys.argv[2]) if len(sys.argv) > 2 else 64
