@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- homogenized Gauss points / second of the RVE-homogenization hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload elastic30|damage50] [--ngp G]
+    python bench.py --impl reference ...      # the reference's own CPU/OpenMP path on the host cores
+
+One "step" = one `homogenize()` pass over the whole resident batch of RVEs (one per macro Gauss point)
+through the reference-facing C ABI of libmicropp_b200.so.  Workloads (BASELINE.json `configs`):
+
+  elastic30 (default; configs[1])  1024 GPs per GPU, 30^3-node RVE, sphere r=0.2, elastic E=1e7/1e8 nu=.3,
+                                   random strains U[-1e-3,1e-3]^6 (seed 1234), lin_stress=false, FE_ONE_WAY.
+  damage50  (configs[2], per-GPU   512 GPs per GPU, 50^3-node RVE, sphere r=0.2, damage matrix E=1e7 nu=.3 Xt=1e5 +
+             shard of 4096/8)      elastic sphere E=3e7, nr_max_its=12, load path eps_11 = s_g*0.1*t, t=k*0.015,
+                                   s_g~U[0.5,1.5] (seed 1234).  Steps 0..5 of the path are run (with update_vars) as
+                                   untimed preparation; every warm-up / timed step is load step 6 from that state
+                                   (update_vars is not called in between, so every step does identical work).
+
+Scaling is weak: every rank owns its own GPs (independent RVEs -- no data-path collective).
+
+JSON keys beyond the base contract:
+  value      GP/s with the device-event time of homogenize() (CUDA events on the library's stream, max over ranks)
+  e2e        GP/s with host buffers through the C ABI: set_strains(host) + homogenize + get_stresses(host), wall clock
+  roofline   the dominant kernel k_spmv_dot (DPCG SpMV fused with p.Ap), CUDA events around every launch in the
+             timed region; algorithmic bytes per RVE application = 1944 B * interior nodes + 48 B * all nodes
+             (243 FP64 values per interior node read once, p read + Ap written; boundary rows are identity rows
+             and carry no matrix traffic).  SURVEY's 664 B/row figure is reported as `achieved_664` for reference.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/libmicropp_ref_omp.so, g++ -O3 -fopenmp) on the box's host
+             cores, same workload, bounded sample of GPs (rank 0, N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+EL = lambda E, nu=0.3: (0, E, nu, 0.0, 0.0, 0.0)
+DM = lambda E, nu, Xt: (2, E, nu, 0.0, 0.0, Xt)
+
+WORKLOADS = {
+    "elastic30": dict(n=30, ngp=1024, prep_steps=0,
+                      params=dict(type=1, geo_params=(0.2, 0.0, 0.0, 0.0), materials=[EL(1e7), EL(1e8), EL(1e7)],
+                                  lin_stress=False, calc_ctan_lin=False),
+                      label="configs[1]: 1024 GPs/GPU, 30^3-node RVE, sphere r=0.2, elastic contrast 10, FE_ONE_WAY"),
+    "damage50": dict(n=50, ngp=512, prep_steps=6,
+                     params=dict(type=1, geo_params=(0.2, 0.0, 0.0, 0.0),
+                                 materials=[DM(1e7, 0.3, 1e5), EL(3e7), EL(3e7)],
+                                 lin_stress=False, calc_ctan_lin=False, nr_max_its=12),
+                     label="configs[2] per-GPU shard: 512 GPs/GPU, 50^3-node RVE, sphere r=0.2, damage matrix + "
+                           "elastic sphere, load step 6/10 from the converged state of step 5"),
+}
+
+
+def strains_for(workload: str, ngp: int, rank: int, step: int) -> np.ndarray:
+    """Synthetic macro strains of GP batch `rank` (seeded: identical for every implementation)."""
+    rng = np.random.default_rng(1234 + 7919 * rank)
+    if workload == "elastic30":
+        return rng.uniform(-1e-3, 1e-3, (ngp, 6))
+    s = rng.uniform(0.5, 1.5, ngp)
+    e = np.zeros((ngp, 6))
+    e[:, 0] = s * 0.1 * 0.015 * step
+    return e
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i] == "Active"})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def spmv_bytes_per_rve(n: int) -> tuple[float, float]:
+    nn, nint = n ** 3, (n - 2) ** 3
+    return 1944.0 * nint + 48.0 * nn, 664.0 * 3 * nn
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, wl, sample_ngp: int, steps: int, warmup: int):
+    """The reference's own CPU path (oracle/_ref, OpenMP over GPs) on a bounded sample of the workload."""
+    from oracle import refpy
+    if not refpy.available(omp=True):
+        raise RuntimeError("oracle/_ref/libmicropp_ref_omp.so missing: run `make -C oracle ref` where "
+                           "/root/reference exists (the file travels with the gpurun snapshot)")
+    cores = host_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    n = wl["n"]
+    p = refpy.default_params(size=(n, n, n), ngp=sample_ngp, **wl["params"])
+    r = refpy.RefMicropp(p, omp=True)
+    name = args.workload
+
+    def step(k):
+        e = strains_for(name, sample_ngp, 0, k)
+        for g in range(sample_ngp):
+            r.set_strain(g, e[g])
+        r.homogenize()
+        return np.array([r.get_stress(g) for g in range(sample_ngp)])
+
+    for k in range(wl["prep_steps"]):
+        step(k)
+        r.update_vars()
+    kk = wl["prep_steps"]
+    for _ in range(warmup):
+        step(kk)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(kk)
+    dt = time.perf_counter() - t0
+    cost = [r.get_cost(g) for g in range(sample_ngp)]
+    r.close()
+    return dict(value=sample_ngp * steps / dt, ms_per_step=dt / steps * 1e3, cores=cores,
+                sample=f"{sample_ngp} of the workload's GPs per step, {steps} timed step(s) after {warmup} warm-up; "
+                       f"mean CG its/GP {np.mean(cost):.1f}; OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}")
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="elastic30")
+    ap.add_argument("--ngp", type=int, default=None, help="GPs per GPU (default: the workload's)")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="GPs in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    steps = args.steps if args.steps is not None else (10 if args.workload == "elastic30" else 3)
+    warmup = max(args.warmup, 0)
+    ngp = args.ngp or wl["ngp"]
+    n = wl["n"]
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and args.impl == "b200":
+        # not under torchrun: launch ourselves the way the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               str(Path(__file__).resolve())] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+
+    base_cfg = {"workload": wl["label"], "name": args.workload, "rve_nodes": f"{n}^3", "gps_per_gpu": ngp,
+                "coupling": "FE_ONE_WAY", "sharding": "independent GPs per rank, no collective",
+                "l2": "inputs exceed L2 (per-RVE ELL matrices: %.1f MB each)" % (1944.0 * n ** 3 / 1e6)}
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        sample = args.cpu_sample or (4 * cores if args.workload == "elastic30" else cores)
+        res = run_reference(args, wl, sample, steps, warmup)
+        line = {"impl": "reference", "metric": "homogenized GPs/sec (DPCG+assembly)", "value": res["value"],
+                "unit": "GP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": base_cfg,
+                "cpu_baseline": {"value": res["value"], "unit": "GP/s", "cores": res["cores"], "kind": "reference",
+                                 "sample": res["sample"]},
+                "e2e": {"value": res["value"], "unit": "GP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import micropp_b200 as M
+    M.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_ctor = time.perf_counter()
+    m = M.Micropp3(M.default_params(size=(n, n, n), ngp=ngp, mpi_rank=local_rank, **wl["params"]))
+    ctor_s = time.perf_counter() - t_ctor
+
+    # pinned host buffers for the boundary crossing (the C ABI takes plain host pointers)
+    eps_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
+    sig_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
+    eps_h, sig_h = eps_pin.numpy(), sig_pin.numpy()
+
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    h = C.byref(m.h)
+    lib = m.lib
+
+    def e2e_step(k):
+        eps_h[:] = strains_for(args.workload, ngp, rank, k)
+        lib.micropp3_set_strains(h, eps_h.ctypes.data_as(dp))
+        lib.micropp3_homogenize(h)
+        lib.micropp3_get_stresses(h, sig_h.ctypes.data_as(dp))
+
+    for k in range(wl["prep_steps"]):
+        e2e_step(k)
+        m.update_vars()
+    kk = wl["prep_steps"]
+    for _ in range(warmup):
+        e2e_step(kk)
+
+    # ---- timed region 1: device-event time of homogenize() with the strains already handed over ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = m.launch_count()
+    m.prof_enable(True)
+    m.prof_read(True)
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.micropp3_homogenize(h)
+        dev_ms += m.last_homogenize_ms()
+    barrier()
+    wall1 = time.perf_counter() - t0
+    prof = m.prof_read(True)
+    m.prof_enable(False)
+    launches = m.launch_count() - launches0
+    cost = np.array([m.get_cost(g) for g in range(ngp)], dtype=np.float64)
+    conv = sum(m.has_converged(g) for g in range(ngp))
+    nl = m.get_non_linear_gps()
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step(kk)
+    barrier()
+    wall2 = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.all(np.isfinite(sig_h)), "non-finite homogenized stress"
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    dev_ms_max = max_over_ranks(dev_ms)
+    wall2_max = max_over_ranks(wall2)
+    total_gps = sum_over_ranks(float(ngp))
+    launches_tot = int(sum_over_ranks(float(launches)))
+
+    # roofline of the dominant kernel (rank 0's launches; every SpMV application of an RVE = one CG iteration)
+    b_alg, b_664 = spmv_bytes_per_rve(n)
+    apps = float(np.sum(cost)) * steps
+    spmv_ms = prof["spmv_ms"]
+    peak, peak_src = hbm_peak()
+    achieved = b_alg * apps / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    roof = {"kernel": "k_spmv_dot (DPCG SpMV + p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "achieved_664": b_664 * apps / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0,
+            "bytes_per_rve_application": b_alg, "rve_applications": apps, "launches": prof["spmv_launches"],
+            "kernel_ms": spmv_ms, "share_of_step": spmv_ms / max(dev_ms, 1e-9),
+            "other_kernels_ms": {"asm_mat": prof["asm_mat_ms"], "asm_rhs": prof["asm_rhs_ms"],
+                                 "cg_vectors": prof["cg_vec_ms"]}}
+    tr = ROOT / "profiles" / "spmv_traffic.json"  # dram bytes per launch from the committed ncu capture
+    if tr.exists():
+        try:
+            roof["traffic"] = json.loads(tr.read_text()).get(args.workload)
+        except Exception:
+            pass
+
+    line = {"metric": "homogenized GPs/sec (DPCG+assembly)", "value": total_gps * steps / (dev_ms_max * 1e-3),
+            "unit": "GP/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms_max / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(base_cfg, newton_cg={"mean_cg_its_per_gp": float(np.mean(cost)), "converged": conv,
+                                                 "non_linear_gps": nl, "wave": m.wave_size()},
+                           ctor_s=ctor_s),
+            "e2e": {"value": total_gps * steps / wall2_max, "unit": "GP/s", "h2d_bytes_per_step": int(ngp * 48),
+                    "d2h_bytes_per_step": int(ngp * 48), "ms_per_step": wall2_max / steps * 1e3},
+            "gpu_launches": launches_tot, "clocks": clocks, "roofline": roof}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = host_cores()
+            sample = args.cpu_sample or (4 * cores if args.workload == "elastic30" else cores)
+            res = run_reference(args, wl, sample, 1, 0)
+            line["cpu_baseline"] = {"value": res["value"], "unit": "GP/s", "cores": res["cores"],
+                                    "kind": "reference", "sample": res["sample"]}
+        except Exception as ex:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "GP/s", "cores": host_cores(), "kind": "reference",
+                                    "sample": f"unavailable: {ex}"}
+    m.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
