@@ -127,8 +127,8 @@ def test_full_size_operator_null_space_and_spmv(mpp, case, n):
     rng = np.random.default_rng(7)
     u = g.set_displ_bc(np.array([0.01, -0.004, 0.002, 0.006, -0.003, 0.001]), rng.uniform(-1e-3, 1e-3, g.nndim))
     A = g.assembly_mat(u)
-    t = np.tile(np.array([1.0, -2.0, 0.5]), g.nn)
-    y = (A.reshape(g.nn, 3, 27, 3) * t.reshape(1, 1, 1, 3)[..., :]).sum(axis=(2, 3))  # all neighbours carry t
+    t3 = np.array([1.0, -2.0, 0.5])
+    y = (A.reshape(g.nn, 3, 27, 3) * t3.reshape(1, 1, 1, 3)).sum(axis=(2, 3))  # every neighbour carries t3
     idx = np.arange(g.nn)
     i, j, k = idx % n, (idx // n) % n, idx // (n * n)
     bnd = (i == 0) | (i == n - 1) | (j == 0) | (j == n - 1) | (k == 0) | (k == n - 1)
