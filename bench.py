@@ -331,7 +331,9 @@ def main():
     tr = ROOT / "profiles" / "spmv_traffic.json"  # dram bytes per launch from the committed ncu capture
     if tr.exists():
         try:
-            roof["traffic"] = json.loads(tr.read_text()).get(args.workload)
+            per_rve = json.loads(tr.read_text())[args.workload]["dram_bytes_per_rve_application"]
+            roof["traffic"] = per_rve * apps / max(prof["spmv_launches"], 1)  # per launch, like `achieved`
+            roof["algorithmic_bytes_per_launch"] = b_alg * apps / max(prof["spmv_launches"], 1)
         except Exception:
             pass
 

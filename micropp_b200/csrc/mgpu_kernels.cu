@@ -394,23 +394,60 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ------------------------------------------------------------------------------------------------
-// assembly_mat, general (damage / plastic / mixed).  8 threads per node: thread (node, c) owns the
-// element c of the 8 around the node and computes the 3 rows of that element's 24x24 matrix that
-// belong to the node, K_rows = sum_gp (G_a^T C_gp wg) B_gp, with C_gp the reference's forward-
-// difference tangent (src/material.cpp:49-63).  The 8 row blocks are then added into a shared-
-// memory image of the node's ELL row in the reference's element order (ex outermost), and the
-// image is written out coalesced: each ELL value is stored to HBM exactly once.
+// assembly_mat, general (damage / plastic / mixed), in two kernels.
+//
+// (1) k_elem_ctan: thread per element.  Gathers the 24 element dofs once and evaluates the reference's
+//     forward-difference tangent (src/material.cpp:49-63: 7 stress evaluations) at the 8 Gauss points,
+//     storing C_gp (36 doubles, row-major) into a scratch buffer laid out [(gp*36+q)][nelem_pad] per
+//     slot of the current chunk, so stores and the later loads are coalesced over elements.  Every
+//     tangent is computed exactly once (a node-gather that recomputes it would do so 8 times).
+// (2) k_asm_mat_general: 8 threads per node: thread (node, c) owns element c of the 8 around the node
+//     and computes the 3 rows of that element's 24x24 matrix that belong to the node,
+//     K_rows = sum_gp (G_a^T C_gp wg) B_gp, reading C_gp from the scratch buffer.  The 8 row blocks
+//     are added into a shared-memory image of the node's ELL row in the reference's element order
+//     (ex outermost), and the image is written out coalesced: each ELL value is stored exactly once.
+// Elastic elements of a mixed RVE take their rows from the precomputed per-material table.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN = 16;  // nodes per block of the general assembly kernel (GN*8 == NT)
+constexpr int GN = 16;      // nodes per block of the gather kernel (GN*8 == NT)
+constexpr int CTAN_LEN = 8 * 36;  // doubles per element in the tangent scratch
 
 __global__ void __launch_bounds__(NT)
-    k_asm_mat_general(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
-                      const double *__restrict__ u_pool, size_t vstride, double *mat_pool, size_t mstride,
-                      double *mat_shared, const int *__restrict__ elem_type, const double *__restrict__ ke_tab) {
-  extern __shared__ double s_acc[];  // [GN][243]
+    k_elem_ctan(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+                const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
+                double *__restrict__ cbuf, size_t cstride) {
   const int slot = list[blockIdx.y];
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
+  double *cb = cbuf + (size_t)blockIdx.y * cstride;
+  const int e = blockIdx.x * NT + threadIdx.x;
+  if (e >= P.nelem) return;
+  const int type = __ldg(&elem_type[e]);
+  const mpp_material m = P.mat[type];
+  if (m.type == MPP_ELASTIC) return;  // rows come from the per-material table
+  const int ez = e / (P.nex * P.ney);
+  const int r = e - ez * P.nex * P.ney;
+  const int ey = r / P.nex, ex = r - ey * P.nex;
+  double ue[24];
+  gather_ue(P, u, ex, ey, ez, ue);
+  const int nv = mat_nvar(m.type);
+#pragma unroll 1
+  for (int gp = 0; gp < 8; ++gp) {
+    double eps[6], C[36], vbuf[7];
+    gp_strain(P.dsh[gp], ue, eps);
+    const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+    mat_ctan(m, eps, v, C);
+#pragma unroll
+    for (int q = 0; q < 36; ++q) cb[(size_t)(gp * 36 + q) * P.nelem_pad + e] = C[q];
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+    k_asm_mat_general(const __grid_constant__ MeshConst P, const int *__restrict__ list, double *mat_pool,
+                      size_t mstride, double *mat_shared, const int *__restrict__ elem_type,
+                      const double *__restrict__ ke_tab, const double *__restrict__ cbuf, size_t cstride) {
+  extern __shared__ double s_acc[];  // [GN][243]
+  const int slot = list[blockIdx.y];
+  const double *cb = cbuf + (size_t)blockIdx.y * cstride;
   double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
 
   for (int q = threadIdx.x; q < GN * NPLANE; q += NT) s_acc[q] = 0.0;
@@ -434,24 +471,20 @@ __global__ void __launch_bounds__(NT)
     a = corner_of(1 - ax, 1 - ay, 1 - az);
     const int e = (ez * P.ney + ey) * P.nex + ex;
     const int type = __ldg(&elem_type[e]);
-    const mpp_material m = P.mat[type];
-    if (m.type == MPP_ELASTIC) {
+    if (P.mat[type].type == MPP_ELASTIC) {
       const double *ke = ke_tab + type * 576 + a * 72;
 #pragma unroll
       for (int q = 0; q < 72; ++q) R[q] = __ldg(&ke[q]);
     } else {
 #pragma unroll
       for (int q = 0; q < 72; ++q) R[q] = 0.0;
-      double ue[24];
-      gather_ue(P, u, ex, ey, ez, ue);
-      const int nv = mat_nvar(m.type);
       const double wg = P.wg;
 #pragma unroll 1
       for (int gp = 0; gp < 8; ++gp) {
-        double eps[6], C[36], vbuf[7];
-        gp_strain(P.dsh[gp], ue, eps);
-        const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
-        mat_ctan(m, eps, v, C);
+        double C[36];
+        const double *cg = cb + (size_t)(gp * 36) * P.nelem_pad + e;
+#pragma unroll
+        for (int q = 0; q < 36; ++q) C[q] = cg[(size_t)q * P.nelem_pad];
         const double gx = P.dsh[gp][a * 3 + 0] * wg, gy = P.dsh[gp][a * 3 + 1] * wg, gz = P.dsh[gp][a * 3 + 2] * wg;
 #pragma unroll
         for (int fi = 0; fi < 3; ++fi) {
@@ -879,6 +912,8 @@ struct mgpu_ctx {
   bool all_elastic = true;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
+  double *d_ctan = nullptr;  // tangent scratch of the general Jacobian assembly: [ctan_chunk][288][nelem_pad]
+  int ctan_chunk = 0;
   VecPool V{};
   SlotTables T{};
   int *d_list[NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1137,6 +1172,13 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   size_t reserve = sizeof(double) * mlen /* A0 */ + (size_t(1) << 30);
+  const size_t ctan_per_slot = sizeof(double) * CTAN_LEN * (size_t)P.nelem_pad;
+  if (!c->all_elastic) {
+    // tangent scratch for a chunk of slots: about 4% of the device, 4..64 slots
+    long long ch = (long long)((total_b / 25) / std::max<size_t>(ctan_per_slot, 1));
+    c->ctan_chunk = (int)std::min<long long>(64, std::max<long long>(4, ch));
+    reserve += ctan_per_slot * c->ctan_chunk;
+  }
   if (!c->all_elastic) reserve += (size_t)ngp * 2 * c->var_len * sizeof(double);
   size_t avail = free_b > reserve ? free_b - reserve : 0;
   avail = (size_t)(avail * 0.92);
@@ -1163,6 +1205,10 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     CK(cudaMemset(*pp, 0, sizeof(double) * vlen * W));
   }
   CK(cudaMalloc(&V.mat, sizeof(double) * mlen * W));
+  if (!c->all_elastic) {
+    c->ctan_chunk = std::min(c->ctan_chunk, (int)W);
+    CK(cudaMalloc(&c->d_ctan, ctan_per_slot * c->ctan_chunk));
+  }
   V.mat_shared = nullptr;  // allocated on first use (use_A0)
 
   SlotTables &T = c->T;
@@ -1220,6 +1266,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   cudaFreeHost(c->h_count);
   cudaFree(c->d_elem_type);
   cudaFree(c->d_ke);
+  if (c->d_ctan) cudaFree(c->d_ctan);
   if (c->d_ustore) cudaFree(c->d_ustore);
   for (auto p : c->var_chunks) cudaFree(p);
   for (int w = 0; w < 2; ++w)
@@ -1384,9 +1431,17 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
     k_asm_mat_elastic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->V.mat, c->V.mstride, shared,
                                                             c->d_elem_type, c->d_ke);
   } else {
-    dim3 g((c->mc.nn + GN - 1) / GN, n);
-    k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
-        c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke);
+    const size_t cstride = (size_t)CTAN_LEN * c->mc.nelem_pad;
+    for (int off = 0; off < n; off += c->ctan_chunk) {
+      const int cnt = std::min(c->ctan_chunk, n - off);
+      const int *lst = c->d_list[l] + off;
+      k_elem_ctan<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
+                                                          c->d_ctan, cstride);
+      dim3 g((c->mc.nn + GN - 1) / GN, cnt);
+      k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
+          c->mc, lst, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke, c->d_ctan, cstride);
+      c->launches += 1;
+    }
   }
   CK(cudaGetLastError());
 }
