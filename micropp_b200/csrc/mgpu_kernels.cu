@@ -211,19 +211,34 @@ __global__ void k_set_bc(const __grid_constant__ MeshConst P, const int *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// assembly_rhs (src/assembly.cpp:28-103): gather by node, elements visited in (ez,ey,ex) order.
+// assembly_rhs (src/assembly.cpp:28-103) in two kernels.
+// (1) k_elem_rhs: thread per element: be = sum_gp B^T sigma wg (get_elem_rhs, src/assembly.cpp:124-138),
+//     every Gauss-point stress evaluated exactly once, stored as [24][nelem_pad] per slot of the chunk.
+// (2) k_asm_rhs: thread per node: adds the contributions of the 8 surrounding elements in the
+//     reference's element visiting order (ez outer, ex inner), zeroes boundary rows, negates, and
+//     reduces ||b||^2 (deterministic ticket reduction) with the Newton loop-head logic in its tail.
 // ------------------------------------------------------------------------------------------------
-template <int A>
-__device__ __forceinline__ void elem_rhs_at_node(const MeshConst &P, const double *__restrict__ u,
-                                                 const double *vars, const int *__restrict__ elem_type, int ex,
-                                                 int ey, int ez, double &bx, double &by, double &bz) {
-  double ue[24];
+__global__ void __launch_bounds__(NT)
+    k_elem_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+               const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
+               double *__restrict__ bebuf, size_t bstride, int mode) {
+  const int slot = list[blockIdx.y];
+  if (mode == 1 && !T.state[slot].nr_active) return;
+  const double *u = u_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  double *be = bebuf + (size_t)blockIdx.y * bstride;
+  const int e = blockIdx.x * NT + threadIdx.x;
+  if (e >= P.nelem) return;
+  const int ez = e / (P.nex * P.ney);
+  const int r = e - ez * P.nex * P.ney;
+  const int ey = r / P.nex, ex = r - ey * P.nex;
+  double ue[24], acc[24];
   gather_ue(P, u, ex, ey, ez, ue);
-  const int e = (ez * P.ney + ey) * P.nex + ex;
+#pragma unroll
+  for (int q = 0; q < 24; ++q) acc[q] = 0.0;
   const int type = __ldg(&elem_type[e]);
   const mpp_material m = P.mat[type];
   const int nv = mat_nvar(m.type);
-  double sx = 0.0, sy = 0.0, sz = 0.0;
   const double wg = P.wg;
 #pragma unroll 1
   for (int gp = 0; gp < 8; ++gp) {
@@ -231,36 +246,36 @@ __device__ __forceinline__ void elem_rhs_at_node(const MeshConst &P, const doubl
     gp_strain(P.dsh[gp], ue, eps);
     const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
     mat_stress(m, eps, v, sig);
-    const double gx = P.dsh[gp][A * 3 + 0], gy = P.dsh[gp][A * 3 + 1], gz = P.dsh[gp][A * 3 + 2];
-    // be[i] += B[gp][j][i] * sig[j] * wg, j ascending (src/assembly.cpp:135-136)
-    sx += gx * sig[0] * wg;
-    sx += gy * sig[3] * wg;
-    sx += gz * sig[4] * wg;
-    sy += gy * sig[1] * wg;
-    sy += gx * sig[3] * wg;
-    sy += gz * sig[5] * wg;
-    sz += gz * sig[2] * wg;
-    sz += gx * sig[4] * wg;
-    sz += gy * sig[5] * wg;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double gx = P.dsh[gp][a * 3 + 0], gy = P.dsh[gp][a * 3 + 1], gz = P.dsh[gp][a * 3 + 2];
+      // be[i] += B[gp][j][i] * sig[j] * wg, j ascending (src/assembly.cpp:135-136)
+      acc[a * 3 + 0] += gx * sig[0] * wg;
+      acc[a * 3 + 0] += gy * sig[3] * wg;
+      acc[a * 3 + 0] += gz * sig[4] * wg;
+      acc[a * 3 + 1] += gy * sig[1] * wg;
+      acc[a * 3 + 1] += gx * sig[3] * wg;
+      acc[a * 3 + 1] += gz * sig[5] * wg;
+      acc[a * 3 + 2] += gz * sig[2] * wg;
+      acc[a * 3 + 2] += gx * sig[4] * wg;
+      acc[a * 3 + 2] += gy * sig[5] * wg;
+    }
   }
-  bx += sx;
-  by += sy;
-  bz += sz;
+#pragma unroll
+  for (int q = 0; q < 24; ++q) be[(size_t)q * P.nelem_pad + e] = acc[q];
 }
 
 // mode 0: first residual of a Newton solve (sets norm0, its=0); 1: after an update (its++); 2: plain
 __global__ void __launch_bounds__(NT)
-    k_asm_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
-              const double *__restrict__ u_pool, double *b_pool, size_t vstride, const int *__restrict__ elem_type,
-              int mode) {
+    k_asm_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, double *b_pool,
+              size_t vstride, const double *__restrict__ bebuf, size_t bstride, int mode) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
   const int slot = list[blockIdx.y];
   mgpu_slot_state *st = &T.state[slot];
   if (mode == 1 && !st->nr_active) return;
-  const double *u = u_pool + (size_t)slot * vstride;
   double *b = b_pool + (size_t)slot * vstride;
-  const double *vars = T.vars_old[slot];
+  const double *be = bebuf + (size_t)blockIdx.y * bstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   double nrm[1] = {0.0};
   if (n < P.nn) {
@@ -269,14 +284,15 @@ __global__ void __launch_bounds__(NT)
     double bx = 0.0, by = 0.0, bz = 0.0;
     if (!on_boundary(P, i, j, k)) {
       // the eight elements around the node in the reference's visiting order (ez outer, ex inner)
-      elem_rhs_at_node<corner_of(1, 1, 1)>(P, u, vars, elem_type, i - 1, j - 1, k - 1, bx, by, bz);
-      elem_rhs_at_node<corner_of(0, 1, 1)>(P, u, vars, elem_type, i, j - 1, k - 1, bx, by, bz);
-      elem_rhs_at_node<corner_of(1, 0, 1)>(P, u, vars, elem_type, i - 1, j, k - 1, bx, by, bz);
-      elem_rhs_at_node<corner_of(0, 0, 1)>(P, u, vars, elem_type, i, j, k - 1, bx, by, bz);
-      elem_rhs_at_node<corner_of(1, 1, 0)>(P, u, vars, elem_type, i - 1, j - 1, k, bx, by, bz);
-      elem_rhs_at_node<corner_of(0, 1, 0)>(P, u, vars, elem_type, i, j - 1, k, bx, by, bz);
-      elem_rhs_at_node<corner_of(1, 0, 0)>(P, u, vars, elem_type, i - 1, j, k, bx, by, bz);
-      elem_rhs_at_node<corner_of(0, 0, 0)>(P, u, vars, elem_type, i, j, k, bx, by, bz);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int az = (c >> 2) & 1, ay = (c >> 1) & 1, ax = c & 1;  // element = (i-1+ax, j-1+ay, k-1+az)
+        const int e = ((k - 1 + az) * P.ney + (j - 1 + ay)) * P.nex + (i - 1 + ax);
+        const int a = corner_of(1 - ax, 1 - ay, 1 - az);
+        bx += be[(size_t)(a * 3 + 0) * P.nelem_pad + e];
+        by += be[(size_t)(a * 3 + 1) * P.nelem_pad + e];
+        bz += be[(size_t)(a * 3 + 2) * P.nelem_pad + e];
+      }
       bx = -bx;
       by = -by;
       bz = -bz;
@@ -912,6 +928,8 @@ struct mgpu_ctx {
   bool all_elastic = true;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
+  double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
+  int be_chunk = 0;
   double *d_ctan = nullptr;  // tangent scratch of the general Jacobian assembly: [ctan_chunk][288][nelem_pad]
   int ctan_chunk = 0;
   VecPool V{};
@@ -1173,6 +1191,12 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   CK(cudaMemGetInfo(&free_b, &total_b));
   size_t reserve = sizeof(double) * mlen /* A0 */ + (size_t(1) << 30);
   const size_t ctan_per_slot = sizeof(double) * CTAN_LEN * (size_t)P.nelem_pad;
+  const size_t be_per_slot = sizeof(double) * 24 * (size_t)P.nelem_pad;
+  {
+    long long ch = (long long)((total_b / 100) / std::max<size_t>(be_per_slot, 1));  // about 1% of the device
+    c->be_chunk = (int)std::min<long long>(256, std::max<long long>(4, ch));
+    reserve += be_per_slot * c->be_chunk;
+  }
   if (!c->all_elastic) {
     // tangent scratch for a chunk of slots: about 4% of the device, 4..64 slots
     long long ch = (long long)((total_b / 25) / std::max<size_t>(ctan_per_slot, 1));
@@ -1205,6 +1229,8 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     CK(cudaMemset(*pp, 0, sizeof(double) * vlen * W));
   }
   CK(cudaMalloc(&V.mat, sizeof(double) * mlen * W));
+  c->be_chunk = std::min(c->be_chunk, (int)W);
+  CK(cudaMalloc(&c->d_be, be_per_slot * c->be_chunk));
   if (!c->all_elastic) {
     c->ctan_chunk = std::min(c->ctan_chunk, (int)W);
     CK(cudaMalloc(&c->d_ctan, ctan_per_slot * c->ctan_chunk));
@@ -1267,6 +1293,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   cudaFree(c->d_elem_type);
   cudaFree(c->d_ke);
   if (c->d_ctan) cudaFree(c->d_ctan);
+  if (c->d_be) cudaFree(c->d_be);
   if (c->d_ustore) cudaFree(c->d_ustore);
   for (auto p : c->var_chunks) cudaFree(p);
   for (int w = 0; w < 2; ++w)
@@ -1414,8 +1441,16 @@ void mgpu_set_bc(mgpu_ctx *c, int l, int n) {
 void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
   if (n <= 0) return;
   ProfScope ps(c, 2, n);
-  k_asm_rhs<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.b, c->V.vstride,
-                                                  c->d_elem_type, mode);
+  const size_t bstride = (size_t)24 * c->mc.nelem_pad;
+  for (int off = 0; off < n; off += c->be_chunk) {
+    const int cnt = std::min(c->be_chunk, n - off);
+    const int *lst = c->d_list[l] + off;
+    k_elem_rhs<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
+                                                       c->d_be, bstride, mode);
+    k_asm_rhs<<<node_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.b, c->V.vstride, c->d_be, bstride,
+                                                      mode);
+    c->launches += 1;
+  }
   CK(cudaGetLastError());
 }
 void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
