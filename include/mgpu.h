@@ -109,6 +109,11 @@ void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);
 /* compaction: list_out <- entries of list_in whose (mode 0: nr_active, 1: cg_active) flag is set; returns count (syncs) */
 int mgpu_compact(mgpu_ctx *, int list_in, int n_in, int list_out, int mode);
 
+/* One whole Newton step (assembly_mat -> DPCG as a device-driven WHILE node -> u += du -> assembly_rhs) as one
+   CUDA graph over list 1 (the Newton list, whose device-side length mgpu_compact(.., 1, ..) maintains).  Returns
+   the number of slots that need another step (syncs once). */
+int mgpu_newton_step_graph(mgpu_ctx *, int n_active, int use_shared);
+
 /* ---- results ---- */
 void mgpu_fetch_state(mgpu_ctx *, int n, const int *slots, mgpu_slot_state *out); /* syncs */
 void mgpu_fetch_stress(mgpu_ctx *, int n, const int *slots, double *sig6);        /* syncs */

@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmicropp_b200.so"
+LIB_PATH = Path(os.environ["MICROPP_B200_LIB"]) if os.environ.get("MICROPP_B200_LIB") else PKG / "libmicropp_b200.so"
 
 # enums of include/types.hpp and include/material_base.h
 MIC = dict(HOMOGENEOUS=0, SPHERE=1, LAYER_Y=2, CILI_FIB_X=3, CILI_FIB_Z=4, CILI_FIB_XZ=5, QUAD_FIB_XYZ=6,

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "fe_math.cuh"
@@ -83,6 +84,27 @@ __device__ __forceinline__ void node_ijk(const MeshConst &P, int n, int &i, int 
 }
 __device__ __forceinline__ bool on_boundary(const MeshConst &P, int i, int j, int k) {
   return i == 0 || i == P.nx - 1 || j == 0 || j == P.ny - 1 || k == 0 || k == P.nz - 1;
+}
+
+// ELL values of one RVE are stored in tiles of 32 consecutive nodes: [tile][243 planes][32 nodes].  A warp that owns
+// one tile streams a single contiguous 62 KB chunk (plane after plane, 256 B per load, immediate offsets from one
+// base register) -- DRAM page locality does not depend on how the compiler schedules the 243 loads.
+__host__ __device__ __forceinline__ size_t aidx(int plane, int node) {
+  return ((size_t)(node >> 5) * NPLANE + plane) * 32 + (node & 31);
+}
+
+// A batched kernel runs over (blocks) x (entries of a slot list).  `dcount` (optional) is a device-side entry
+// count: inside a captured CUDA graph the launch shape is fixed while the number of still-active slots shrinks,
+// so surplus blocks leave at once.  `yoff` is the offset of this launch inside the list (chunked launches).
+struct Lst {
+  const int *list;
+  const int *dcount;
+  int yoff;
+};
+__device__ __forceinline__ int slot_of(const Lst &L) {
+  const int y = (int)blockIdx.y + L.yoff;
+  if (L.dcount && y >= *L.dcount) return -1;
+  return L.list[y];
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -164,26 +186,29 @@ __device__ __forceinline__ void gather_ue(const MeshConst &P, const double *__re
 // ------------------------------------------------------------------------------------------------
 // u <- u_n / u_k ; u_k <- u
 // ------------------------------------------------------------------------------------------------
-__global__ void k_load_u(MeshConst P, const int *__restrict__ list, SlotTables T, double *u_pool, size_t vstride,
+__global__ void k_load_u(MeshConst P, const Lst L, SlotTables T, double *u_pool, size_t vstride,
                          int which) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   const double *src = which ? T.u_k[slot] : T.u_n[slot];
   double *dst = u_pool + (size_t)slot * vstride;
   const int len = 3 * P.nn_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-__global__ void k_store_u(MeshConst P, const int *__restrict__ list, SlotTables T, const double *u_pool,
+__global__ void k_store_u(MeshConst P, const Lst L, SlotTables T, const double *u_pool,
                           size_t vstride, int which) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   double *dst = which ? T.u_k[slot] : T.u_n[slot];
   const double *src = u_pool + (size_t)slot * vstride;
   const int len = 3 * P.nn_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-__global__ void k_zero_u(MeshConst P, const int *__restrict__ list, double *u_pool, size_t vstride) {
-  const int slot = list[blockIdx.y];
+__global__ void k_zero_u(MeshConst P, const Lst L, double *u_pool, size_t vstride) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   double *dst = u_pool + (size_t)slot * vstride;
   const int len = 3 * P.nn_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) dst[i] = 0.0;
@@ -192,9 +217,10 @@ __global__ void k_zero_u(MeshConst P, const int *__restrict__ list, double *u_po
 // ------------------------------------------------------------------------------------------------
 // set_displ_bc (src/micro3D.cpp:27-78)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_set_bc(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+__global__ void k_set_bc(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                          double *u_pool, size_t vstride) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= P.nn) return;
   int i, j, k;
@@ -219,10 +245,11 @@ __global__ void k_set_bc(const __grid_constant__ MeshConst P, const int *__restr
 //     reduces ||b||^2 (deterministic ticket reduction) with the Newton loop-head logic in its tail.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
-    k_elem_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+    k_elem_rhs(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
                double *__restrict__ bebuf, size_t bstride, int mode) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   if (mode == 1 && !T.state[slot].nr_active) return;
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
@@ -267,11 +294,12 @@ __global__ void __launch_bounds__(NT)
 
 // mode 0: first residual of a Newton solve (sets norm0, its=0); 1: after an update (its++); 2: plain
 __global__ void __launch_bounds__(NT)
-    k_asm_rhs(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, double *b_pool,
+    k_asm_rhs(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, double *b_pool,
               size_t vstride, const double *__restrict__ bebuf, size_t bstride, int mode) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (mode == 1 && !st->nr_active) return;
   double *b = b_pool + (size_t)slot * vstride;
@@ -362,7 +390,7 @@ __device__ __forceinline__ void asm_elastic_slot(const double *__restrict__ s_ke
   double acc[9];
   gather_block_elastic<DI, DJ, DK>(s_ke, et, acc);
 #pragma unroll
-  for (int q = 0; q < 9; ++q) A[(size_t)(NBR * 9 + q) * nn_pad + n] = acc[q];
+  for (int q = 0; q < 9; ++q) A[aidx(NBR * 9 + q, n)] = acc[q];
 }
 
 template <int NBR>
@@ -379,13 +407,14 @@ struct AsmElasticLoop<27> {
 };
 
 __global__ void __launch_bounds__(NT)
-    k_asm_mat_elastic(const __grid_constant__ MeshConst P, const int *__restrict__ list, double *mat_pool,
+    k_asm_mat_elastic(const __grid_constant__ MeshConst P, const Lst L, double *mat_pool,
                       size_t mstride, double *mat_shared, const int *__restrict__ elem_type,
                       const double *__restrict__ ke_tab) {
   __shared__ double s_ke[3 * 576];
   for (int q = threadIdx.x; q < 3 * 576; q += NT) s_ke[q] = ke_tab[q];
   __syncthreads();
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   if (n >= P.nn) return;
@@ -396,7 +425,7 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll 9
     for (int pl = 0; pl < NPLANE; ++pl) {
       const int q = pl - 13 * 9;
-      A[(size_t)pl * P.nn_pad + n] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;
+      A[aidx(pl, n)] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;
     }
     return;
   }
@@ -428,10 +457,11 @@ constexpr int GN = 16;      // nodes per block of the gather kernel (GN*8 == NT)
 constexpr int CTAN_LEN = 8 * 36;  // doubles per element in the tangent scratch
 
 __global__ void __launch_bounds__(NT)
-    k_elem_ctan(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+    k_elem_ctan(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                 const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
                 double *__restrict__ cbuf, size_t cstride) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
   double *cb = cbuf + (size_t)blockIdx.y * cstride;
@@ -458,11 +488,12 @@ __global__ void __launch_bounds__(NT)
 }
 
 __global__ void __launch_bounds__(NT)
-    k_asm_mat_general(const __grid_constant__ MeshConst P, const int *__restrict__ list, double *mat_pool,
+    k_asm_mat_general(const __grid_constant__ MeshConst P, const Lst L, double *mat_pool,
                       size_t mstride, double *mat_shared, const int *__restrict__ elem_type,
                       const double *__restrict__ ke_tab, const double *__restrict__ cbuf, size_t cstride) {
   extern __shared__ double s_acc[];  // [GN][243]
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   const double *cb = cbuf + (size_t)blockIdx.y * cstride;
   double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
 
@@ -553,7 +584,7 @@ __global__ void __launch_bounds__(NT)
   for (int q = threadIdx.x; q < GN * NPLANE; q += NT) {
     const int pl = q / GN, l = q % GN;
     const int nd = blockIdx.x * GN + l;
-    if (nd < P.nn) A[(size_t)pl * P.nn_pad + nd] = s_acc[l * NPLANE + pl];
+    if (nd < P.nn) A[aidx(pl, nd)] = s_acc[l * NPLANE + pl];
   }
 }
 
@@ -561,11 +592,12 @@ __global__ void __launch_bounds__(NT)
 // DPCG (src/ell.cpp:66-122)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
-    k_cg_init(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V,
+    k_cg_init(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V,
               int use_shared) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   const double *A = use_shared ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
   const size_t vo = (size_t)slot * V.vstride;
@@ -575,7 +607,7 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double diag = A[(size_t)(13 * 9 + d * 4) * P.nn_pad + n];
+      const double diag = A[aidx(13 * 9 + d * 4, n)];
       const double kk = 1 / diag;  // src/ell.cpp:73-76
       const double r = V.b[ix];    // r = b - A*0 (src/ell.cpp:78-82)
       const double z = kk * r;
@@ -608,16 +640,16 @@ __device__ __forceinline__ void spmv_slot(const double *__restrict__ A, const do
   constexpr int DI = NBR % 3 - 1, DJ = (NBR / 3) % 3 - 1, DK = NBR / 9 - 1;
   const int m = n + DI + DJ * nx + DK * nxny;
   const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
-  const double *a = A + (size_t)(NBR * 9) * npad + n;
+  const double *a = A + aidx(NBR * 9, n);  // planes of one tile are 32 doubles apart
   y0 += a[0] * px;
-  y0 += a[npad] * py;
-  y0 += a[2 * npad] * pz;
-  y1 += a[3 * npad] * px;
-  y1 += a[4 * npad] * py;
-  y1 += a[5 * npad] * pz;
-  y2 += a[6 * npad] * px;
-  y2 += a[7 * npad] * py;
-  y2 += a[8 * npad] * pz;
+  y0 += a[32] * py;
+  y0 += a[64] * pz;
+  y1 += a[96] * px;
+  y1 += a[128] * py;
+  y1 += a[160] * pz;
+  y2 += a[192] * px;
+  y2 += a[224] * py;
+  y2 += a[256] * pz;
 }
 template <int NBR>
 struct SpmvLoop {
@@ -646,16 +678,16 @@ __device__ __forceinline__ void spmv_row_checked(const MeshConst &P, const doubl
     if (ii < 0 || ii >= P.nx || jj < 0 || jj >= P.ny || kk < 0 || kk >= P.nz) continue;
     const int m = n + di + dj * P.nx + dk * P.nxny;
     const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
-    const double *a = A + (size_t)(nbr * 9) * npad + n;
+    const double *a = A + aidx(nbr * 9, n);
     y0 += a[0] * px;
-    y0 += a[npad] * py;
-    y0 += a[2 * npad] * pz;
-    y1 += a[3 * npad] * px;
-    y1 += a[4 * npad] * py;
-    y1 += a[5 * npad] * pz;
-    y2 += a[6 * npad] * px;
-    y2 += a[7 * npad] * py;
-    y2 += a[8 * npad] * pz;
+    y0 += a[32] * py;
+    y0 += a[64] * pz;
+    y1 += a[96] * px;
+    y1 += a[128] * py;
+    y1 += a[160] * pz;
+    y2 += a[192] * px;
+    y2 += a[224] * py;
+    y2 += a[256] * pz;
   }
 }
 
@@ -663,11 +695,12 @@ __device__ __forceinline__ void spmv_row_checked(const MeshConst &P, const doubl
 // GENERIC = true : arbitrary user matrix (host-pointer ell_mvp / ell_solve_cgpd API).
 template <bool GENERIC>
 __global__ void __launch_bounds__(NT)
-    k_spmv_dot(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V,
+    k_spmv_dot(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V,
                int use_shared, int force) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!force && !st->cg_active) return;
   const double *A = use_shared ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
@@ -708,10 +741,11 @@ __global__ void __launch_bounds__(NT)
 // x += alpha p ; r -= alpha Ap ; z = k r ; z.z ; r.z   (src/ell.cpp:102-110), then the scalar tail
 // of the iteration and the loop-head test of the next one (src/ell.cpp:93-94,108-119).
 __global__ void __launch_bounds__(NT)
-    k_cg_update(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
+    k_cg_update(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
   const double alpha = st->alpha;
@@ -746,8 +780,9 @@ __global__ void __launch_bounds__(NT)
 
 // p = z + beta p (src/ell.cpp:113); skipped once the slot has left the loop (p is dead then).
 __global__ void __launch_bounds__(NT)
-    k_cg_pupdate(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
-  const int slot = list[blockIdx.y];
+    k_cg_pupdate(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   const mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
   const double beta = st->beta;
@@ -763,8 +798,9 @@ __global__ void __launch_bounds__(NT)
 
 // u += du (src/solve.cpp:73) and newton.solver_its += cg_its (src/solve.cpp:71)
 __global__ void __launch_bounds__(NT)
-    k_axpy_u(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T, VecPool V) {
-  const int slot = list[blockIdx.y];
+    k_axpy_u(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!st->nr_active) return;
   const size_t vo = (size_t)slot * V.vstride;
@@ -782,11 +818,12 @@ __global__ void __launch_bounds__(NT)
 // calc_ave_stress (src/average.cpp:58-82): thread per element
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
-    k_ave_stress(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+    k_ave_stress(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                  const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
@@ -822,9 +859,10 @@ __global__ void __launch_bounds__(NT)
 // calc_vars_new (src/update.cpp:33-56): thread per element; write = 0 only raises the non-linear flag
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
-    k_vars_new(const __grid_constant__ MeshConst P, const int *__restrict__ list, SlotTables T,
+    k_vars_new(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type, int write) {
-  const int slot = list[blockIdx.y];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
@@ -865,7 +903,13 @@ __global__ void k_clear_nl(const int *__restrict__ list, int n, SlotTables T) {
 // ------------------------------------------------------------------------------------------------
 // stable compaction of a slot list by an activity flag (single block)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_compact(const int *in, int n_in, int *out, int *count, SlotTables T, int mode) {
+// n_in_dev (optional): device-side length of `in`; count2 (optional): second destination of the new length;
+// inside a graph the kernel also drives the WHILE node (cond_set) and counts loop trips (trips).  in == out is
+// allowed: every entry of a chunk is read before the barrier that precedes the chunk's writes, and writes never
+// run ahead of reads.
+__global__ void k_compact(const int *in, int n_in, const int *n_in_dev, int *out, int *count, int *count2,
+                          SlotTables T, int mode, cudaGraphConditionalHandle cond, int cond_set, int *trips) {
+  if (n_in_dev) n_in = *n_in_dev;
   __shared__ int s_warp[32];
   __shared__ int s_base;
   if (threadIdx.x == 0) s_base = 0;
@@ -893,7 +937,12 @@ __global__ void k_compact(const int *in, int n_in, int *out, int *count, SlotTab
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = s_base;
+  if (threadIdx.x == 0) {
+    if (count) *count = s_base;
+    if (count2) *count2 = s_base;
+    if (trips) *trips += 1;
+    if (cond_set) cudaGraphSetConditional(cond, s_base > 0 ? 1u : 0u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -936,6 +985,8 @@ struct mgpu_ctx {
   SlotTables T{};
   int *d_list[NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int *d_count = nullptr;
+  int *d_cnt2 = nullptr;           // device-side list lengths used inside graphs: [0] Newton list, [1] CG list
+  const int *dyn_count = nullptr;  // non-null while a graph is being captured: launches test it per block
   int *h_count = nullptr;  // pinned
   // persistent per-GP state
   double *d_ustore = nullptr;  // [ngp][2][3*nn_pad]
@@ -960,10 +1011,16 @@ struct mgpu_ctx {
   double prof_acc[6] = {0, 0, 0, 0, 0, 0};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   unsigned long long launches = 0;
+  struct StepGraph {
+    cudaGraphExec_t exec;
+    int fixed_launches, body_launches;
+  };
+  std::map<long long, StepGraph> step_graphs;  // key = bucket * 2 + use_shared
 };
 
 namespace {
 
+inline Lst lst_of(const mgpu_ctx *c, int l, int off = 0) { return Lst{c->d_list[l], c->dyn_count, off}; }
 inline dim3 node_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT - 1) / NT, n, 1); }
 inline dim3 elem_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nelem + NT - 1) / NT, n, 1); }
 
@@ -1252,7 +1309,9 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   CK(cudaMalloc(&T.partial, sizeof(double) * (size_t)NRED * nblk_max * W));
   for (int l = 0; l < NLIST; ++l) CK(cudaMalloc(&c->d_list[l], sizeof(int) * W));
   CK(cudaMalloc(&c->d_count, sizeof(int)));
-  CK(cudaMallocHost(&c->h_count, sizeof(int)));
+  CK(cudaMallocHost(&c->h_count, 4 * sizeof(int)));
+  CK(cudaMalloc(&c->d_cnt2, 4 * sizeof(int)));
+  CK(cudaMemset(c->d_cnt2, 0, 4 * sizeof(int)));
 
   c->slot_gp.assign(W, -1);
   c->h_vars_old.assign(W, nullptr);
@@ -1290,6 +1349,8 @@ void mgpu_destroy(mgpu_ctx *c) {
   for (int l = 0; l < NLIST; ++l) cudaFree(c->d_list[l]);
   cudaFree(c->d_count);
   cudaFreeHost(c->h_count);
+  cudaFree(c->d_cnt2);
+  for (auto &kv : c->step_graphs) cudaGraphExecDestroy(kv.second.exec);
   cudaFree(c->d_elem_type);
   cudaFree(c->d_ke);
   if (c->d_ctan) cudaFree(c->d_ctan);
@@ -1413,7 +1474,7 @@ void mgpu_load_u(mgpu_ctx *c, int l, int n, int which_u) {
   ProfScope ps(c, 9, n);
   const int len = 3 * c->mc.nn_pad;
   dim3 g(std::min((len + 255) / 256, 1024), n);
-  k_load_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, which_u);
+  k_load_u<<<g, 256, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride, which_u);
   CK(cudaGetLastError());
 }
 void mgpu_store_u(mgpu_ctx *c, int l, int n, int which_u) {
@@ -1421,7 +1482,7 @@ void mgpu_store_u(mgpu_ctx *c, int l, int n, int which_u) {
   ProfScope ps(c, 9, n);
   const int len = 3 * c->mc.nn_pad;
   dim3 g(std::min((len + 255) / 256, 1024), n);
-  k_store_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride, which_u);
+  k_store_u<<<g, 256, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride, which_u);
   CK(cudaGetLastError());
 }
 void mgpu_zero_u(mgpu_ctx *c, int l, int n) {
@@ -1429,13 +1490,13 @@ void mgpu_zero_u(mgpu_ctx *c, int l, int n) {
   ProfScope ps(c, 9, n);
   const int len = 3 * c->mc.nn_pad;
   dim3 g(std::min((len + 255) / 256, 1024), n);
-  k_zero_u<<<g, 256, 0, c->stream>>>(c->mc, c->d_list[l], c->V.u, c->V.vstride);
+  k_zero_u<<<g, 256, 0, c->stream>>>(c->mc, lst_of(c, l), c->V.u, c->V.vstride);
   CK(cudaGetLastError());
 }
 void mgpu_set_bc(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_set_bc<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride);
+  k_set_bc<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride);
   CK(cudaGetLastError());
 }
 void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
@@ -1444,7 +1505,7 @@ void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
   const size_t bstride = (size_t)24 * c->mc.nelem_pad;
   for (int off = 0; off < n; off += c->be_chunk) {
     const int cnt = std::min(c->be_chunk, n - off);
-    const int *lst = c->d_list[l] + off;
+    const Lst lst = lst_of(c, l, off);
     k_elem_rhs<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
                                                        c->d_be, bstride, mode);
     k_asm_rhs<<<node_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.b, c->V.vstride, c->d_be, bstride,
@@ -1463,13 +1524,13 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
   }
   ProfScope ps(c, 1, n);
   if (c->all_elastic) {
-    k_asm_mat_elastic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->V.mat, c->V.mstride, shared,
+    k_asm_mat_elastic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->V.mat, c->V.mstride, shared,
                                                             c->d_elem_type, c->d_ke);
   } else {
     const size_t cstride = (size_t)CTAN_LEN * c->mc.nelem_pad;
     for (int off = 0; off < n; off += c->ctan_chunk) {
       const int cnt = std::min(c->ctan_chunk, n - off);
-      const int *lst = c->d_list[l] + off;
+      const Lst lst = lst_of(c, l, off);
       k_elem_ctan<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
                                                           c->d_ctan, cstride);
       dim3 g((c->mc.nn + GN - 1) / GN, cnt);
@@ -1483,44 +1544,44 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
-  k_cg_init<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, use_shared);
+  k_cg_init<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared);
   CK(cudaGetLastError());
 }
 void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
-  k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, use_shared, 0);
+  k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
   CK(cudaGetLastError());
 }
 void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
-  k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
-  k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V);
+  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_ave_stress(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_ave_stress<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride,
+  k_ave_stress<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride,
                                                      c->d_elem_type);
   CK(cudaGetLastError());
 }
 void mgpu_vars_new(mgpu_ctx *c, int l, int n, int write) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_vars_new<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V.u, c->V.vstride,
+  k_vars_new<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride,
                                                    c->d_elem_type, write);
   CK(cudaGetLastError());
 }
@@ -1533,11 +1594,121 @@ void mgpu_clear_nl_flags(mgpu_ctx *c, int l, int n) {
 int mgpu_compact(mgpu_ctx *c, int list_in, int n_in, int list_out, int mode) {
   if (n_in <= 0) return 0;
   c->launches++;
-  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in], n_in, c->d_list[list_out], c->d_count, c->T, mode);
+  // lists 1 (Newton) and 2 (CG) keep their length on the device too: the step graphs start from it
+  int *count2 = list_out == 1 ? c->d_cnt2 : (list_out == 2 ? c->d_cnt2 + 1 : nullptr);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in], n_in, nullptr, c->d_list[list_out], c->d_count, count2, c->T,
+                                       mode, cudaGraphConditionalHandle(), 0, nullptr);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return *c->h_count;
+}
+
+// ---- one Newton step as ONE CUDA graph --------------------------------------------------------------
+// assembly_mat -> cg_init -> WHILE(any slot still iterating){ SpMV+dot ; x,r,z update ; p update ; compaction }
+// -> u += du -> assembly_rhs (+ Newton loop-head test) -> compaction of the Newton list, for all slots of the
+// Newton list at once (src/solve.cpp:49-77 with src/ell.cpp:93-119 inside).  The DPCG loop is a conditional WHILE
+// node driven from the device (cudaGraphSetConditional in k_compact), so the host is not involved between the
+// start of a Newton step and its end.  Launch shapes are fixed per graph (bucket = power of two >= active slots);
+// blocks beyond the device-side list length leave immediately (Lst::dcount).
+namespace {
+
+void capture_begin(mgpu_ctx *c, cudaGraph_t g, const cudaGraphNode_t *deps, size_t ndeps) {
+  CK(cudaStreamBeginCaptureToGraph(c->stream, g, deps, nullptr, ndeps, cudaStreamCaptureModeRelaxed));
+}
+// ends the capture and returns the leaf nodes captured so far (dependencies of whatever comes next)
+std::vector<cudaGraphNode_t> capture_end(mgpu_ctx *c) {
+  cudaStreamCaptureStatus st;
+  const cudaGraphNode_t *deps = nullptr;
+  size_t nd = 0;
+  CK(cudaStreamGetCaptureInfo_v2(c->stream, &st, nullptr, nullptr, &deps, &nd));
+  std::vector<cudaGraphNode_t> out(deps, deps + nd);
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamEndCapture(c->stream, &g));
+  return out;
+}
+
+mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
+  const bool prof = c->prof;
+  c->prof = false;  // no event records inside a capture
+  const unsigned long long l0 = c->launches;
+  cudaGraph_t g;
+  CK(cudaGraphCreate(&g, 0));
+  cudaGraphConditionalHandle cond;
+  CK(cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
+
+  // head: Jacobian, CG start, CG list := Newton-list slots whose loop-head test says "iterate"
+  capture_begin(c, g, nullptr, 0);
+  c->dyn_count = c->d_cnt2;
+  if (!use_shared) mgpu_asm_mat(c, 1, B, 0);
+  mgpu_cg_init(c, 1, B, use_shared);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[2], c->d_cnt2 + 1, nullptr, c->T, 1, cond,
+                                       1, nullptr);
+  c->launches++;
+  std::vector<cudaGraphNode_t> leaves = capture_end(c);
+  const int head = (int)(c->launches - l0);
+
+  // the DPCG loop
+  cudaGraphNodeParams wp = {};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = cond;
+  wp.conditional.type = cudaGraphCondTypeWhile;
+  wp.conditional.size = 1;
+  cudaGraphNode_t wnode;
+  CK(cudaGraphAddNode(&wnode, g, leaves.data(), leaves.size(), &wp));
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  const unsigned long long l1 = c->launches;
+  capture_begin(c, body, nullptr, 0);
+  c->dyn_count = c->d_cnt2 + 1;
+  mgpu_cg_spmv_dot(c, 2, B, use_shared);
+  mgpu_cg_update(c, 2, B);
+  mgpu_cg_pupdate(c, 2, B);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[2], 0, c->d_cnt2 + 1, c->d_list[2], c->d_cnt2 + 1, nullptr, c->T, 1,
+                                       cond, 1, c->d_cnt2 + 2);
+  c->launches++;
+  capture_end(c);
+  const int body_l = (int)(c->launches - l1);
+
+  // tail: update, residual + Newton test, Newton list compaction, list lengths to the host
+  const unsigned long long l2 = c->launches;
+  capture_begin(c, g, &wnode, 1);
+  c->dyn_count = c->d_cnt2;
+  mgpu_axpy_u(c, 1, B);
+  mgpu_asm_rhs(c, 1, B, 1);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[1], c->d_cnt2, nullptr, c->T, 0, cond, 0,
+                                       nullptr);
+  c->launches++;
+  CK(cudaMemcpyAsync(c->h_count, c->d_cnt2, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  capture_end(c);
+  const int tail = (int)(c->launches - l2);
+  c->dyn_count = nullptr;
+  c->launches = l0;  // captured, not executed
+  c->prof = prof;
+
+  mgpu_ctx::StepGraph sg;
+  CK(cudaGraphInstantiate(&sg.exec, g, 0));
+  CK(cudaGraphDestroy(g));
+  sg.fixed_launches = head + tail;
+  sg.body_launches = body_l;
+  return sg;
+}
+
+}  // namespace
+
+extern "C" int mgpu_newton_step_graph(mgpu_ctx *c, int n_active, int use_shared) {
+  if (n_active <= 0) return 0;
+  CK(cudaSetDevice(c->device));
+  int B = 1;
+  while (B < n_active) B <<= 1;
+  B = std::min(B, c->W);
+  const long long key = (long long)B * 2 + (use_shared ? 1 : 0);
+  auto it = c->step_graphs.find(key);
+  if (it == c->step_graphs.end()) it = c->step_graphs.emplace(key, build_step_graph(c, B, use_shared)).first;
+  CK(cudaMemsetAsync(c->d_cnt2 + 2, 0, sizeof(int), c->stream));
+  CK(cudaGraphLaunch(it->second.exec, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches += it->second.fixed_launches + (unsigned long long)it->second.body_launches * c->h_count[2];
+  return c->h_count[0];
 }
 
 // ---- results ----------------------------------------------------------------------------------
@@ -1626,7 +1797,7 @@ void mgpu_stage_get_mat(mgpu_ctx *c, int slot, double *vals) {
     for (int nbr = 0; nbr < 27; ++nbr)
       for (int fi = 0; fi < 3; ++fi)
         for (int fj = 0; fj < 3; ++fj)
-          vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] = tmp[(size_t)(nbr * 9 + fi * 3 + fj) * npad + n];
+          vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] = tmp[aidx(nbr * 9 + fi * 3 + fj, n)];
 }
 void mgpu_stage_put_mat(mgpu_ctx *c, int slot, const double *vals) {
   CK(cudaSetDevice(c->device));
@@ -1637,7 +1808,7 @@ void mgpu_stage_put_mat(mgpu_ctx *c, int slot, const double *vals) {
     for (int nbr = 0; nbr < 27; ++nbr)
       for (int fi = 0; fi < 3; ++fi)
         for (int fj = 0; fj < 3; ++fj)
-          tmp[(size_t)(nbr * 9 + fi * 3 + fj) * npad + n] = vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj];
+          tmp[aidx(nbr * 9 + fi * 3 + fj, n)] = vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj];
   CK(cudaMemcpy(c->V.mat + (size_t)slot * c->V.mstride, tmp.data(), sizeof(double) * c->V.mstride,
                 cudaMemcpyHostToDevice));
 }
@@ -1662,7 +1833,7 @@ void mgpu_ell_cols(int nx, int ny, int nz, int *cols, int device) {
 void mgpu_spmv_generic(mgpu_ctx *c, int l, int n, int force) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
-  k_spmv_dot<true><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[l], c->T, c->V, 0, force);
+  k_spmv_dot<true><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, 0, force);
   CK(cudaGetLastError());
 }
 
@@ -1692,11 +1863,11 @@ float mgpu_bench_spmv(mgpu_ctx *c, int n, int iters) {
   for (int i = 0; i < n; ++i) ids[i] = i;
   mgpu_set_list(c, 5, n, ids.data());
   for (int w = 0; w < 2; ++w) {
-    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[5], c->T, c->V, 0, 1);
+    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
   }
   CK(cudaEventRecord(c->t0, c->stream));
   for (int it = 0; it < iters; ++it) {
-    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, c->d_list[5], c->T, c->V, 0, 1);
+    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
   }
   CK(cudaEventRecord(c->t1, c->stream));
   CK(cudaEventSynchronize(c->t1));

@@ -188,6 +188,7 @@ micropp<3>::micropp(const micropp_params_t &params)
   engine->use_A0 = use_A0;
   engine->its_with_A0 = its_with_A0;
   if (const char *env = getenv("MICROPP_CG_CHUNK")) engine->cg_chunk = std::max(1, atoi(env));
+  if (const char *env = getenv("MICROPP_GRAPHS")) engine->use_graphs = atoi(env) != 0;
 
   if (use_A0) {
     // linear Jacobian at u = 0 without history (src/micropp.cpp:128-143): one shared device matrix
@@ -848,6 +849,7 @@ int micropp3x_vars_new(micropp3 *s, const double *u, const double *vars_old, dou
 }
 
 void micropp3x_prof_enable(micropp3 *s, int on) {
+  mpp_access::engine((micropp<3> *)s->ptr)->profiling = on != 0;  // per-kernel events need plain stream launches
   mgpu_prof_enable(mpp_access::engine((micropp<3> *)s->ptr)->ctx, on);
 }
 void micropp3x_prof_read(micropp3 *s, double *out6, int reset) {

@@ -15,6 +15,8 @@ struct mpp_engine {
   int its_with_A0 = 1;
   bool A0_ready = false;
   int cg_chunk = 8;
+  bool use_graphs = true;  // one CUDA graph per Newton step (MICROPP_GRAPHS=0: plain stream launches)
+  bool profiling = false;  // per-kernel CUDA-event timing needs plain launches
 
   // device slot lists: 0 = caller's list, 1 = Newton-active, 2/4 = CG-active (ping-pong), 3 = caller's subset
   enum { L_OUTER = 0, L_NEWTON = 1, L_CG_A = 2, L_SUB = 3, L_CG_B = 4 };
@@ -49,12 +51,17 @@ struct mpp_engine {
     for (;;) {
       const int na = mgpu_compact(ctx, list, n, L_NEWTON, 0);
       if (na == 0) break;
-      int shared = 0;
-      if (use_A0 && A0_ready && it <= its_with_A0 - 1) {
-        shared = 1;  // linear Jacobian for the first its_with_A0 iterations (src/solve.cpp:56-66)
-      } else {
-        mgpu_asm_mat(ctx, L_NEWTON, na, 0);
+      // linear Jacobian for the first its_with_A0 iterations (src/solve.cpp:56-66)
+      const int shared = (use_A0 && A0_ready && it <= its_with_A0 - 1) ? 1 : 0;
+      if (use_graphs && !profiling) {
+        int left = na;
+        while (left > 0) {  // every graph launch is one Newton step of all still-active slots
+          left = mgpu_newton_step_graph(ctx, left, (use_A0 && A0_ready && it <= its_with_A0 - 1) ? 1 : 0);
+          ++it;
+        }
+        break;
       }
+      if (!shared) mgpu_asm_mat(ctx, L_NEWTON, na, 0);
       cg_solve(L_NEWTON, na, shared);
       mgpu_axpy_u(ctx, L_NEWTON, na);
       mgpu_asm_rhs(ctx, L_NEWTON, na, 1);

@@ -43,8 +43,9 @@ for s in range(steps):
     m.update_vars()
 m.prof_enable(False)
 m.set_strains(eps)
-t0 = time.time(); m.homogenize(); wall = time.time() - t0
-print(f"no-prof: wall {wall*1e3:.1f} ms  GP/s {ngp/wall:.1f}  launches so far {m.launch_count()}")
+for rep in range(3):
+    t0 = time.time(); m.homogenize(); wall = time.time() - t0
+    print(f"no-prof[{rep}]: wall {wall*1e3:.2f} ms  GP/s {ngp/wall:.1f}  launches so far {m.launch_count()}")
 ms = m.bench_spmv(min(ngp, m.wave_size()), 10)
 nb = min(ngp, m.wave_size())
 print(f"isolated spmv: {ms:.3f} ms for {nb} slots => {664.0*3*n**3*nb/ms/1e6:.0f} GB/s algorithmic")
