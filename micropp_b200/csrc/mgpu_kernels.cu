@@ -45,6 +45,7 @@ constexpr int NRED = 6;      // max values reduced per kernel
 
 struct MeshConst {
   int nx, ny, nz, nxny, nn, nn_pad;
+  int nix, niy, niz, nint, nint_pad;  // interior nodes (the only rows the ELL storage keeps)
   int nex, ney, nez, nelem, nelem_pad;
   int nvar;
   int nr_max_its, cg_max_its;
@@ -68,8 +69,9 @@ struct SlotTables {  // device arrays, one entry per slot
 
 struct VecPool {
   double *u, *b, *du, *k, *r, *z, *p, *Ap;  // [W][3*nn_pad]
-  double *mat;                              // [W][243*nn_pad]
-  double *mat_shared;                       // [243*nn_pad] (A0)
+  double *mat;                              // [W][243*nint_pad], interior rows, 32-node tiles
+  double *mat_shared;                       // [243*nint_pad] (A0)
+  double *gen;                              // [3*nn][81] host matrix of the generic ELL API (reference layout)
   size_t vstride, mstride;
 };
 
@@ -82,11 +84,24 @@ __device__ __forceinline__ void node_ijk(const MeshConst &P, int n, int &i, int 
   j = r / P.nx;
   i = r - j * P.nx;
 }
+// interior-node index m (x fastest) -> grid coordinates and global node id
+__device__ __forceinline__ int interior_node(const MeshConst &P, int m, int &i, int &j, int &k) {
+  const int pl = P.nix * P.niy;
+  const int kk = m / pl, r = m - kk * pl, jj = r / P.nix;
+  i = r - jj * P.nix + 1;
+  j = jj + 1;
+  k = kk + 1;
+  return k * P.nxny + j * P.nx + i;
+}
+__device__ __forceinline__ int interior_index(const MeshConst &P, int i, int j, int k) {
+  return ((k - 1) * P.niy + (j - 1)) * P.nix + (i - 1);
+}
 __device__ __forceinline__ bool on_boundary(const MeshConst &P, int i, int j, int k) {
   return i == 0 || i == P.nx - 1 || j == 0 || j == P.ny - 1 || k == 0 || k == P.nz - 1;
 }
 
-// ELL values of one RVE are stored in tiles of 32 consecutive nodes: [tile][243 planes][32 nodes].  A warp that owns
+// ELL values of one RVE are stored for INTERIOR nodes only (boundary rows are identity rows, ell_set_bc_3D
+// src/ell-common.cpp:238-297, and are never read) in tiles of 32 consecutive interior nodes: [tile][243 planes][32].  A warp that owns
 // one tile streams a single contiguous 62 KB chunk (plane after plane, 256 B per load, immediate offsets from one
 // base register) -- DRAM page locality does not depend on how the compiler schedules the 243 loads.
 __host__ __device__ __forceinline__ size_t aidx(int plane, int node) {
@@ -416,26 +431,17 @@ __global__ void __launch_bounds__(NT)
   const int slot = slot_of(L);
   if (slot < 0) return;
   double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
-  const int n = blockIdx.x * NT + threadIdx.x;
-  if (n >= P.nn) return;
+  const int m = blockIdx.x * NT + threadIdx.x;
+  if (m >= P.nint) return;
   int i, j, k;
-  node_ijk(P, n, i, j, k);
-  if (on_boundary(P, i, j, k)) {
-    // ell_set_bc_3D (src/ell-common.cpp:238-297): identity rows
-#pragma unroll 9
-    for (int pl = 0; pl < NPLANE; ++pl) {
-      const int q = pl - 13 * 9;
-      A[aidx(pl, n)] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;
-    }
-    return;
-  }
+  interior_node(P, m, i, j, k);
   int et[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int ex = i - 1 + ((c >> 2) & 1), ey = j - 1 + ((c >> 1) & 1), ez = k - 1 + (c & 1);
     et[c] = __ldg(&elem_type[(ez * P.ney + ey) * P.nex + ex]);
   }
-  AsmElasticLoop<0>::run(s_ke, et, A, (size_t)P.nn_pad, n);
+  AsmElasticLoop<0>::run(s_ke, et, A, (size_t)P.nint_pad, m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,14 +507,10 @@ __global__ void __launch_bounds__(NT)
   __syncthreads();
 
   const int ln = threadIdx.x >> 3, c = threadIdx.x & 7;
-  const int n = blockIdx.x * GN + ln;
+  const int m = blockIdx.x * GN + ln;  // interior-node index
   int i = 0, j = 0, k = 0;
-  bool valid = n < P.nn, bnd = false;
-  if (valid) {
-    node_ijk(P, n, i, j, k);
-    bnd = on_boundary(P, i, j, k);
-  }
-  const bool work = valid && !bnd;
+  const bool work = m < P.nint;
+  if (work) interior_node(P, m, i, j, k);
 
   double R[72];
   int a = 0;
@@ -574,17 +576,10 @@ __global__ void __launch_bounds__(NT)
     }
     __syncthreads();
   }
-  if (valid && bnd && c == 0) {
-    double *row = s_acc + ln * NPLANE;
-    row[13 * 9 + 0] = 1.0;
-    row[13 * 9 + 4] = 1.0;
-    row[13 * 9 + 8] = 1.0;
-  }
-  __syncthreads();
   for (int q = threadIdx.x; q < GN * NPLANE; q += NT) {
     const int pl = q / GN, l = q % GN;
-    const int nd = blockIdx.x * GN + l;
-    if (nd < P.nn) A[aidx(pl, nd)] = s_acc[l * NPLANE + pl];
+    const int md = blockIdx.x * GN + l;
+    if (md < P.nint) A[aidx(pl, md)] = s_acc[l * NPLANE + pl];
   }
 }
 
@@ -599,15 +594,24 @@ __global__ void __launch_bounds__(NT)
   const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
-  const double *A = use_shared ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
+  // use_shared: 0 per-slot matrix, 1 the shared linear matrix (A0), 2 the generic host matrix (reference layout)
+  const double *A = use_shared == 1 ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   double red[2] = {0.0, 0.0};
   if (n < P.nn) {
+    int i, j, k;
+    node_ijk(P, n, i, j, k);
+    const bool bnd = on_boundary(P, i, j, k);
+    const int m = bnd ? 0 : interior_index(P, i, j, k);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double diag = A[aidx(13 * 9 + d * 4, n)];
+      double diag = 1.0;  // boundary rows are identity rows (ell_set_bc_3D)
+      if (use_shared == 2)
+        diag = V.gen[((size_t)n * 3 + d) * 81 + 13 * 3 + d];
+      else if (!bnd)
+        diag = A[aidx(13 * 9 + d * 4, m)];
       const double kk = 1 / diag;  // src/ell.cpp:73-76
       const double r = V.b[ix];    // r = b - A*0 (src/ell.cpp:78-82)
       const double z = kk * r;
@@ -616,6 +620,7 @@ __global__ void __launch_bounds__(NT)
       V.r[ix] = r;
       V.z[ix] = z;
       V.p[ix] = z;
+      V.Ap[ix] = 0.0;  // boundary entries of Ap are never written by the SpMV (p is 0 there)
       red[0] += r * z;
       red[1] += z * z;
     }
@@ -632,32 +637,33 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
-// Ap = A p fused with p.Ap.  Thread per node: 3 rows, 243 coalesced value loads (one per plane),
-// 81 p loads that hit L1 (each p value is reused by 27 nodes x 3 rows).
+// Ap = A p fused with p.Ap.  Thread per INTERIOR node: 3 rows, 243 coalesced value loads (one 256-B warp load per
+// plane of the node's tile, immediate offsets), 81 p loads that hit L1 (each p value is reused by 27 nodes x 3
+// rows).  Boundary rows are identity rows with p = 0 (b and x0 vanish there), so they contribute nothing.
 template <int NBR>
-__device__ __forceinline__ void spmv_slot(const double *__restrict__ A, const double *__restrict__ p, size_t npad,
+__device__ __forceinline__ void spmv_slot(const double *__restrict__ a, const double *__restrict__ p, size_t npad,
                                           int n, int nx, int nxny, double &y0, double &y1, double &y2) {
   constexpr int DI = NBR % 3 - 1, DJ = (NBR / 3) % 3 - 1, DK = NBR / 9 - 1;
-  const int m = n + DI + DJ * nx + DK * nxny;
-  const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
-  const double *a = A + aidx(NBR * 9, n);  // planes of one tile are 32 doubles apart
-  y0 += a[0] * px;
-  y0 += a[32] * py;
-  y0 += a[64] * pz;
-  y1 += a[96] * px;
-  y1 += a[128] * py;
-  y1 += a[160] * pz;
-  y2 += a[192] * px;
-  y2 += a[224] * py;
-  y2 += a[256] * pz;
+  const int q = n + DI + DJ * nx + DK * nxny;
+  const double px = p[q], py = p[npad + q], pz = p[2 * npad + q];
+  constexpr int o = NBR * 9 * 32;  // planes of one tile are 32 doubles apart
+  y0 += a[o + 0] * px;
+  y0 += a[o + 32] * py;
+  y0 += a[o + 64] * pz;
+  y1 += a[o + 96] * px;
+  y1 += a[o + 128] * py;
+  y1 += a[o + 160] * pz;
+  y2 += a[o + 192] * px;
+  y2 += a[o + 224] * py;
+  y2 += a[o + 256] * pz;
 }
 template <int NBR>
 struct SpmvLoop {
-  static __device__ __forceinline__ void run(const double *__restrict__ A, const double *__restrict__ p,
+  static __device__ __forceinline__ void run(const double *__restrict__ a, const double *__restrict__ p,
                                              size_t npad, int n, int nx, int nxny, double &y0, double &y1,
                                              double &y2) {
-    spmv_slot<NBR>(A, p, npad, n, nx, nxny, y0, y1, y2);
-    SpmvLoop<NBR + 1>::run(A, p, npad, n, nx, nxny, y0, y1, y2);
+    spmv_slot<NBR>(a, p, npad, n, nx, nxny, y0, y1, y2);
+    SpmvLoop<NBR + 1>::run(a, p, npad, n, nx, nxny, y0, y1, y2);
   }
 };
 template <>
@@ -666,37 +672,8 @@ struct SpmvLoop<27> {
                                              int, int, double &, double &, double &) {}
 };
 
-// Generic row (any node, neighbours outside the grid skipped -- their stored value is 0 and the
-// reference multiplies it by x[fj], src/ell-common.cpp:102-130 + src/ell.cpp:39-41).
-__device__ __forceinline__ void spmv_row_checked(const MeshConst &P, const double *__restrict__ A,
-                                                 const double *__restrict__ p, int n, int i, int j, int k,
-                                                 double &y0, double &y1, double &y2) {
-  const size_t npad = P.nn_pad;
-  for (int nbr = 0; nbr < 27; ++nbr) {
-    const int di = nbr % 3 - 1, dj = (nbr / 3) % 3 - 1, dk = nbr / 9 - 1;
-    const int ii = i + di, jj = j + dj, kk = k + dk;
-    if (ii < 0 || ii >= P.nx || jj < 0 || jj >= P.ny || kk < 0 || kk >= P.nz) continue;
-    const int m = n + di + dj * P.nx + dk * P.nxny;
-    const double px = p[m], py = p[npad + m], pz = p[2 * npad + m];
-    const double *a = A + aidx(nbr * 9, n);
-    y0 += a[0] * px;
-    y0 += a[32] * py;
-    y0 += a[64] * pz;
-    y1 += a[96] * px;
-    y1 += a[128] * py;
-    y1 += a[160] * pz;
-    y2 += a[192] * px;
-    y2 += a[224] * py;
-    y2 += a[256] * pz;
-  }
-}
-
-// GENERIC = false: Newton path, boundary rows are known identity rows (ell_set_bc_3D) => Ap = p there.
-// GENERIC = true : arbitrary user matrix (host-pointer ell_mvp / ell_solve_cgpd API).
-template <bool GENERIC>
 __global__ void __launch_bounds__(NT)
-    k_spmv_dot(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V,
-               int use_shared, int force) {
+    k_spmv_dot(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int use_shared, int force) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
   const int slot = slot_of(L);
@@ -707,34 +684,65 @@ __global__ void __launch_bounds__(NT)
   const size_t vo = (size_t)slot * V.vstride;
   const double *p = V.p + vo;
   double *Ap = V.Ap + vo;
-  const int n = blockIdx.x * NT + threadIdx.x;
+  const int m = blockIdx.x * NT + threadIdx.x;
   double red[1] = {0.0};
-  if (n < P.nn) {
+  if (m < P.nint) {
     int i, j, k;
-    node_ijk(P, n, i, j, k);
+    const int n = interior_node(P, m, i, j, k);
     double y0 = 0.0, y1 = 0.0, y2 = 0.0;
     const size_t npad = P.nn_pad;
-    const double p0 = p[n], p1 = p[npad + n], p2 = p[2 * npad + n];
-    if (on_boundary(P, i, j, k)) {
-      if (GENERIC) {
-        spmv_row_checked(P, A, p, n, i, j, k, y0, y1, y2);
-      } else {
-        y0 = p0;
-        y1 = p1;
-        y2 = p2;
-      }
-    } else {
-      SpmvLoop<0>::run(A, p, npad, n, P.nx, P.nxny, y0, y1, y2);
-    }
+    SpmvLoop<0>::run(A + aidx(0, m), p, npad, n, P.nx, P.nxny, y0, y1, y2);
     Ap[n] = y0;
     Ap[npad + n] = y1;
     Ap[2 * npad + n] = y2;
-    red[0] = p0 * y0 + p1 * y1 + p2 * y2;
+    red[0] = p[n] * y0 + p[npad + n] * y1 + p[2 * npad + n] * y2;
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<1>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
     st->pAp = red[0];
     st->alpha = st->rz / red[0];  // src/ell.cpp:100
+  }
+}
+
+// Arbitrary user matrix in the reference's own layout vals[row*81 + slot] (host-pointer ell_mvp / ell_solve_cgpd
+// API): every row is read, neighbours outside the grid are skipped -- their stored value is 0 and the reference
+// multiplies it by x[fj] (src/ell-common.cpp:102-130 + src/ell.cpp:39-41).  Test-size utility, not the hot path.
+__global__ void __launch_bounds__(NT)
+    k_spmv_generic(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int force) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!force && !st->cg_active) return;
+  const size_t vo = (size_t)slot * V.vstride;
+  const double *p = V.p + vo;
+  double *Ap = V.Ap + vo;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double red[1] = {0.0};
+  if (n < P.nn) {
+    int i, j, k;
+    node_ijk(P, n, i, j, k);
+    const size_t npad = P.nn_pad;
+    double y[3] = {0.0, 0.0, 0.0};
+    for (int nbr = 0; nbr < 27; ++nbr) {
+      const int di = nbr % 3 - 1, dj = (nbr / 3) % 3 - 1, dk = nbr / 9 - 1;
+      const int ii = i + di, jj = j + dj, kk = k + dk;
+      if (ii < 0 || ii >= P.nx || jj < 0 || jj >= P.ny || kk < 0 || kk >= P.nz) continue;
+      const int q = n + di + dj * P.nx + dk * P.nxny;
+      const double px[3] = {p[q], p[npad + q], p[2 * npad + q]};
+      for (int fi = 0; fi < 3; ++fi)
+        for (int fj = 0; fj < 3; ++fj) y[fi] += V.gen[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] * px[fj];
+    }
+    Ap[n] = y[0];
+    Ap[npad + n] = y[1];
+    Ap[2 * npad + n] = y[2];
+    red[0] = p[n] * y[0] + p[npad + n] * y[1] + p[2 * npad + n] * y[2];
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<1>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    st->pAp = red[0];
+    st->alpha = st->rz / red[0];
   }
 }
 
@@ -1021,6 +1029,7 @@ struct mgpu_ctx {
 namespace {
 
 inline Lst lst_of(const mgpu_ctx *c, int l, int off = 0) { return Lst{c->d_list[l], c->dyn_count, off}; }
+inline dim3 int_grid(const mgpu_ctx *c, int n) { return dim3(std::max((c->mc.nint + NT - 1) / NT, 1), n, 1); }
 inline dim3 node_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT - 1) / NT, n, 1); }
 inline dim3 elem_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nelem + NT - 1) / NT, n, 1); }
 
@@ -1170,6 +1179,11 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   P.nxny = P.nx * P.ny;
   P.nn = P.nx * P.ny * P.nz;
   P.nn_pad = (P.nn + 31) / 32 * 32;
+  P.nix = std::max(P.nx - 2, 0);
+  P.niy = std::max(P.ny - 2, 0);
+  P.niz = std::max(P.nz - 2, 0);
+  P.nint = P.nix * P.niy * P.niz;
+  P.nint_pad = std::max((P.nint + 31) / 32 * 32, 32);
   P.nex = P.nx - 1;
   P.ney = P.ny - 1;
   P.nez = P.nz - 1;
@@ -1241,7 +1255,7 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   }
 
   // wave size from the HBM left after reserving room for internal variables of every GP
-  const size_t mlen = (size_t)NPLANE * P.nn_pad;
+  const size_t mlen = (size_t)NPLANE * P.nint_pad;
   const int nblk_max = std::max((P.nn + NT - 1) / NT, (P.nelem + NT - 1) / NT);
   const size_t per_slot = sizeof(double) * (mlen + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256;
   size_t free_b = 0, total_b = 0;
@@ -1292,7 +1306,9 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     c->ctan_chunk = std::min(c->ctan_chunk, (int)W);
     CK(cudaMalloc(&c->d_ctan, ctan_per_slot * c->ctan_chunk));
   }
+  CK(cudaMemsetAsync(V.mat, 0, sizeof(double) * mlen * W, c->stream));  // tile padding stays defined
   V.mat_shared = nullptr;  // allocated on first use (use_A0)
+  V.gen = nullptr;         // allocated on first use (generic host-matrix API)
 
   SlotTables &T = c->T;
   T.nblk_max = nblk_max;
@@ -1338,6 +1354,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   double *vecs[9] = {c->V.u, c->V.b, c->V.du, c->V.k, c->V.r, c->V.z, c->V.p, c->V.Ap, c->V.mat};
   for (auto p : vecs) cudaFree(p);
   if (c->V.mat_shared) cudaFree(c->V.mat_shared);
+  if (c->V.gen) cudaFree(c->V.gen);
   cudaFree(c->T.state);
   cudaFree((void *)c->T.vars_old);
   cudaFree((void *)c->T.vars_new);
@@ -1518,13 +1535,16 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
   if (n <= 0) return;
   double *shared = nullptr;
   if (to_shared) {
-    if (!c->V.mat_shared) CK(cudaMalloc(&c->V.mat_shared, sizeof(double) * c->V.mstride));
+    if (!c->V.mat_shared) {
+      CK(cudaMalloc(&c->V.mat_shared, sizeof(double) * c->V.mstride));
+      CK(cudaMemsetAsync(c->V.mat_shared, 0, sizeof(double) * c->V.mstride, c->stream));
+    }
     shared = c->V.mat_shared;
     n = 1;
   }
   ProfScope ps(c, 1, n);
   if (c->all_elastic) {
-    k_asm_mat_elastic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->V.mat, c->V.mstride, shared,
+    k_asm_mat_elastic<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->V.mat, c->V.mstride, shared,
                                                             c->d_elem_type, c->d_ke);
   } else {
     const size_t cstride = (size_t)CTAN_LEN * c->mc.nelem_pad;
@@ -1533,7 +1553,7 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
       const Lst lst = lst_of(c, l, off);
       k_elem_ctan<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
                                                           c->d_ctan, cstride);
-      dim3 g((c->mc.nn + GN - 1) / GN, cnt);
+      dim3 g(std::max((c->mc.nint + GN - 1) / GN, 1), cnt);
       k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
           c->mc, lst, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke, c->d_ctan, cstride);
       c->launches += 1;
@@ -1550,7 +1570,7 @@ void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
 void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
-  k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
+  k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
   CK(cudaGetLastError());
 }
 void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
@@ -1788,29 +1808,35 @@ void mgpu_stage_get_vars_new(mgpu_ctx *c, int slot, double *ref) {
 void mgpu_stage_get_mat(mgpu_ctx *c, int slot, double *vals) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  const int nn = c->mc.nn, npad = c->mc.nn_pad;
+  const MeshConst &P = c->mc;
   std::vector<double> tmp(c->V.mstride);
   CK(cudaMemcpy(tmp.data(), c->V.mat + (size_t)slot * c->V.mstride, sizeof(double) * c->V.mstride,
                 cudaMemcpyDeviceToHost));
-  // reference layout: vals[(3n+fi)*81 + nbr*3 + fj]
-  for (int n = 0; n < nn; ++n)
-    for (int nbr = 0; nbr < 27; ++nbr)
-      for (int fi = 0; fi < 3; ++fi)
-        for (int fj = 0; fj < 3; ++fj)
-          vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] = tmp[aidx(nbr * 9 + fi * 3 + fj, n)];
+  // reference layout: vals[(3n+fi)*81 + nbr*3 + fj]; boundary rows are the identity rows of ell_set_bc_3D
+  memset(vals, 0, sizeof(double) * (size_t)P.nn * 3 * 81);
+  for (int k = 0; k < P.nz; ++k)
+    for (int j = 0; j < P.ny; ++j)
+      for (int i = 0; i < P.nx; ++i) {
+        const int n = k * P.nxny + j * P.nx + i;
+        if (i == 0 || i == P.nx - 1 || j == 0 || j == P.ny - 1 || k == 0 || k == P.nz - 1) {
+          for (int d = 0; d < 3; ++d) vals[((size_t)n * 3 + d) * 81 + 13 * 3 + d] = 1.0;
+          continue;
+        }
+        const int m = ((k - 1) * P.niy + (j - 1)) * P.nix + (i - 1);
+        for (int nbr = 0; nbr < 27; ++nbr)
+          for (int fi = 0; fi < 3; ++fi)
+            for (int fj = 0; fj < 3; ++fj)
+              vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj] = tmp[aidx(nbr * 9 + fi * 3 + fj, m)];
+      }
 }
+// host matrix of the generic ELL API (ell_mvp / ell_solve_cgpd on caller-provided values): kept as it is
 void mgpu_stage_put_mat(mgpu_ctx *c, int slot, const double *vals) {
+  (void)slot;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  const int nn = c->mc.nn, npad = c->mc.nn_pad;
-  std::vector<double> tmp(c->V.mstride, 0.0);
-  for (int n = 0; n < nn; ++n)
-    for (int nbr = 0; nbr < 27; ++nbr)
-      for (int fi = 0; fi < 3; ++fi)
-        for (int fj = 0; fj < 3; ++fj)
-          tmp[aidx(nbr * 9 + fi * 3 + fj, n)] = vals[((size_t)n * 3 + fi) * 81 + nbr * 3 + fj];
-  CK(cudaMemcpy(c->V.mat + (size_t)slot * c->V.mstride, tmp.data(), sizeof(double) * c->V.mstride,
-                cudaMemcpyHostToDevice));
+  const size_t len = (size_t)c->mc.nn * 3 * 81;
+  if (!c->V.gen) CK(cudaMalloc(&c->V.gen, sizeof(double) * len));
+  CK(cudaMemcpy(c->V.gen, vals, sizeof(double) * len, cudaMemcpyHostToDevice));
 }
 
 void mgpu_ell_cols(int nx, int ny, int nz, int *cols, int device) {
@@ -1833,7 +1859,7 @@ void mgpu_ell_cols(int nx, int ny, int nz, int *cols, int device) {
 void mgpu_spmv_generic(mgpu_ctx *c, int l, int n, int force) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
-  k_spmv_dot<true><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, 0, force);
+  k_spmv_generic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, force);
   CK(cudaGetLastError());
 }
 
@@ -1863,11 +1889,11 @@ float mgpu_bench_spmv(mgpu_ctx *c, int n, int iters) {
   for (int i = 0; i < n; ++i) ids[i] = i;
   mgpu_set_list(c, 5, n, ids.data());
   for (int w = 0; w < 2; ++w) {
-    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
+    k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
   }
   CK(cudaEventRecord(c->t0, c->stream));
   for (int it = 0; it < iters; ++it) {
-    k_spmv_dot<false><<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
+    k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, 5), c->T, c->V, 0, 1);
   }
   CK(cudaEventRecord(c->t1, c->stream));
   CK(cudaEventSynchronize(c->t1));
