@@ -20,8 +20,10 @@
  *
  * Device data layout (all FP64):
  *   vectors  : per slot, structure-of-arrays by displacement component: v[d*nn_pad + node]
- *   matrix   : per slot, 243 planes of nn_pad doubles: A[(nbr*9 + fi*3 + fj)*nn_pad + node]
- *              (nbr = 27-point stencil slot of src/ell-common.cpp:102-130; column indices implicit)
+ *   matrix   : per slot, INTERIOR rows only (boundary rows are the identity rows of ell_set_bc_3D and are neither
+ *              stored nor read), in tiles of 32 consecutive interior nodes:
+ *              A[((m/32)*243 + nbr*9 + fi*3 + fj)*32 + m%32], m = interior-node index (x fastest),
+ *              nbr = 27-point stencil slot of src/ell-common.cpp:102-130; column indices are implicit
  *   int.vars : per Gauss point of the macro mesh, v[(var*8 + gp)*nelem_pad + elem], var < nvar
  */
 #ifndef MGPU_H
