@@ -146,7 +146,8 @@ def run_reference(args, wl, sample_ngp: int, steps: int, warmup: int):
         raise RuntimeError("oracle/_ref/libmicropp_ref_omp.so missing: run `make -C oracle ref` where "
                            "/root/reference exists (the file travels with the gpurun snapshot)")
     cores = host_cores()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("MICROPP_REF_THREADS", str(cores))
     n = wl["n"]
     p = refpy.default_params(size=(n, n, n), ngp=sample_ngp, **wl["params"])
     r = refpy.RefMicropp(p, omp=True)
