@@ -64,6 +64,10 @@ typedef struct mgpu_config {
   int cg_max_its;
   double cg_abs_tol, cg_rel_tol;
   int wave_cap;               /* max slots (0 = size from free HBM) */
+  /* z-slab of a larger RVE (all zero = a whole RVE).  nz above is the LOCAL plane count including halo planes;
+     local plane k is global plane k + koff of nz_glob; halo_lo/halo_hi: the first/last local plane belongs to the
+     neighbour rank; element layers [ez_own_lo, ez_own_hi) (local numbering) are the ones this rank averages. */
+  int slab, koff, nz_glob, halo_lo, halo_hi, ez_own_lo, ez_own_hi;
 } mgpu_config;
 
 /* ---- context ---- */
@@ -115,6 +119,14 @@ int mgpu_compact(mgpu_ctx *, int list_in, int n_in, int list_out, int mode);
    CUDA graph over list 1 (the Newton list, whose device-side length mgpu_compact(.., 1, ..) maintains).  Returns
    the number of slots that need another step (syncs once). */
 int mgpu_newton_step_graph(mgpu_ctx *, int n_active, int use_shared);
+
+/* ---- slab mode (one RVE split in z-slabs over several GPUs): the caller all-reduces the slab-local sums between a
+   reducing kernel and its scalar tail, and exchanges the halo planes of p before every SpMV ---- */
+void mgpu_tail(mgpu_ctx *, int which_list, int n, int kind /*0 rhs,1 cg_init,2 spmv,3 cg_update,4 ave_stress*/, int mode);
+/* raw device pointers for the exchange: which 0..5 = b,du,Ap,p,u,r of slot 0 ([3][nn_pad]); 10 = slab sums
+   ([W][8] doubles); 11 = averaged stress ([W][6]) */
+void *mgpu_dev_ptr(mgpu_ctx *, int which);
+void *mgpu_stream(mgpu_ctx *);   /* the cudaStream_t every launch of this context goes to */
 
 /* ---- results ---- */
 void mgpu_fetch_state(mgpu_ctx *, int n, const int *slots, mgpu_slot_state *out); /* syncs */

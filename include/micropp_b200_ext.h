@@ -72,6 +72,11 @@ void micropp3x_elem_nodes(int nx, int ny, int ex, int ey, int ez, int *n8);
 /* colour of an element in the 8-colour structured ordering: (ex&1) + 2(ey&1) + 4(ez&1) */
 int micropp3x_elem_colour(int ex, int ey, int ez);
 
+/* z-slab of one large RVE (single RVE split over several GPUs; no counterpart in the reference): device context
+   of the node planes [z0, z1) of the nx x ny x nz grid in `params->size` plus one halo plane towards each
+   neighbour.  Returns an `mgpu_ctx *` (include/mgpu.h) that the caller drives; see micropp_b200/slab.py. */
+struct mgpu_ctx *micropp3x_slab_create(const struct micropp3_params *params, int z0, int z1, int device);
+
 /* measurement (CUDA events on the library's own stream) */
 void micropp3x_prof_enable(struct micropp3 *self, int on);
 void micropp3x_prof_read(struct micropp3 *self, double *out6, int reset);

@@ -46,6 +46,10 @@ constexpr int NRED = 6;      // max values reduced per kernel
 struct MeshConst {
   int nx, ny, nz, nxny, nn, nn_pad;
   int nix, niy, niz, nint, nint_pad;  // interior nodes (the only rows the ELL storage keeps)
+  // z-slab of a larger RVE (single-RVE domain decomposition): local plane k is global plane k + koff; the first /
+  // last local plane is a halo plane (owned by the neighbour rank) when halo_lo / halo_hi is set, else a true face.
+  // Reductions then stop at the slab-local sum (T.red) and the scalar tails run after the cross-rank all-reduce.
+  int slab, koff, nz_glob, halo_lo, halo_hi, ez_own_lo, ez_own_hi;
   int nex, ney, nez, nelem, nelem_pad;
   int nvar;
   int nr_max_its, cg_max_its;
@@ -64,6 +68,7 @@ struct SlotTables {  // device arrays, one entry per slot
   double *eps;     // [W][6]
   double *stress;  // [W][6]
   double *partial; // [W][NRED][nblk_max]
+  double *red;     // [W][8] slab-local sums handed to the all-reduce (slab mode)
   int nblk_max;
 };
 
@@ -199,6 +204,61 @@ __device__ __forceinline__ void gather_ue(const MeshConst &P, const double *__re
 }
 
 // ------------------------------------------------------------------------------------------------
+// scalar tails of the reducing kernels: the reference's per-solve scalar logic, one thread per slot.
+// In slab mode they run from k_tail after the cross-rank all-reduce of T.red.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool true_boundary(const MeshConst &P, int i, int j, int k) {
+  const int kg = k + P.koff;
+  return i == 0 || i == P.nx - 1 || j == 0 || j == P.ny - 1 || kg == 0 || kg == P.nz_glob - 1;
+}
+
+// mode 0: first residual of a Newton solve (sets norm0, its=0); 1: after an update (its++); 2: plain
+__device__ __forceinline__ void tail_rhs(const MeshConst &P, mgpu_slot_state *st, double nrm2, int mode) {
+  const double norm = sqrt(nrm2);
+  st->norm = norm;
+  if (mode == 2) return;
+  int its;
+  if (mode == 0) {
+    st->norm0 = norm;
+    st->nr_its = its = 0;
+    st->solver_its = 0;
+    st->converged = 0;
+  } else {
+    its = ++st->nr_its;
+  }
+  // loop head of src/solve.cpp:43-47 -- no test once nr_max_its solves have been spent
+  int active = 0;
+  if (its < P.nr_max_its) {
+    if (norm < P.nr_max_tol || norm < st->norm0 * P.nr_rel_tol)
+      st->converged = 1;
+    else
+      active = 1;
+  }
+  st->nr_active = active;
+}
+__device__ __forceinline__ void tail_cg_init(const MeshConst &P, mgpu_slot_state *st, double rz, double zz) {
+  const double pn = sqrt(zz);
+  st->rz = rz;
+  st->pnorm0 = pn;
+  st->pnorm = pn;
+  st->cg_its = 0;
+  // loop head of src/ell.cpp:93-94
+  st->cg_active = (0 < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < pn * P.cg_rel_tol);
+}
+__device__ __forceinline__ void tail_spmv(mgpu_slot_state *st, double pAp) {
+  st->pAp = pAp;
+  st->alpha = st->rz / pAp;  // src/ell.cpp:100
+}
+__device__ __forceinline__ void tail_cg_update(const MeshConst &P, mgpu_slot_state *st, double zz, double rz_n) {
+  const double pn = sqrt(zz);
+  st->pnorm = pn;
+  st->beta = rz_n / st->rz;
+  st->rz = rz_n;
+  const int its = ++st->cg_its;
+  st->cg_active = (its < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < st->pnorm0 * P.cg_rel_tol);
+}
+
+// ------------------------------------------------------------------------------------------------
 // u <- u_n / u_k ; u_k <- u
 // ------------------------------------------------------------------------------------------------
 __global__ void k_load_u(MeshConst P, const Lst L, SlotTables T, double *u_pool, size_t vstride,
@@ -240,11 +300,11 @@ __global__ void k_set_bc(const __grid_constant__ MeshConst P, const Lst L, SlotT
   if (n >= P.nn) return;
   int i, j, k;
   node_ijk(P, n, i, j, k);
-  if (!on_boundary(P, i, j, k)) return;
+  if (!true_boundary(P, i, j, k)) return;  // halo planes of a slab are interior nodes of the RVE
   double eps[6], c[3], u3[3];
 #pragma unroll
   for (int q = 0; q < 6; ++q) eps[q] = T.eps[slot * 6 + q];
-  bc_coords(i, j, k, P.nx, P.ny, P.nz, P.dx, P.dy, P.dz, c);
+  bc_coords(i, j, k + P.koff, P.nx, P.ny, P.nz_glob, P.dx, P.dy, P.dz, c);
   bc_displacement(eps, c, u3);
   double *u = u_pool + (size_t)slot * vstride;
 #pragma unroll
@@ -347,27 +407,10 @@ __global__ void __launch_bounds__(NT)
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<1>(nrm, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    const double norm = sqrt(nrm[0]);
-    st->norm = norm;
-    if (mode == 2) return;
-    int its;
-    if (mode == 0) {
-      st->norm0 = norm;
-      st->nr_its = its = 0;
-      st->solver_its = 0;
-      st->converged = 0;
-    } else {
-      its = ++st->nr_its;
-    }
-    // loop head of src/solve.cpp:43-47 -- no test once nr_max_its solves have been spent
-    int active = 0;
-    if (its < P.nr_max_its) {
-      if (norm < P.nr_max_tol || norm < st->norm0 * P.nr_rel_tol)
-        st->converged = 1;
-      else
-        active = 1;
-    }
-    st->nr_active = active;
+    if (P.slab)
+      T.red[slot * 8] = nrm[0];
+    else
+      tail_rhs(P, st, nrm[0], mode);
   }
 }
 
@@ -627,13 +670,12 @@ __global__ void __launch_bounds__(NT)
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    const double pn = sqrt(red[1]);
-    st->rz = red[0];
-    st->pnorm0 = pn;
-    st->pnorm = pn;
-    st->cg_its = 0;
-    // loop head of src/ell.cpp:93-94
-    st->cg_active = (0 < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < pn * P.cg_rel_tol);
+    if (P.slab) {
+      T.red[slot * 8] = red[0];
+      T.red[slot * 8 + 1] = red[1];
+    } else {
+      tail_cg_init(P, st, red[0], red[1]);
+    }
   }
 }
 
@@ -699,8 +741,10 @@ __global__ void __launch_bounds__(NT)
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<1>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    st->pAp = red[0];
-    st->alpha = st->rz / red[0];  // src/ell.cpp:100
+    if (P.slab)
+      T.red[slot * 8] = red[0];
+    else
+      tail_spmv(st, red[0]);
   }
 }
 
@@ -741,8 +785,7 @@ __global__ void __launch_bounds__(NT)
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<1>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    st->pAp = red[0];
-    st->alpha = st->rz / red[0];
+    tail_spmv(st, red[0]);
   }
 }
 
@@ -776,13 +819,12 @@ __global__ void __launch_bounds__(NT)
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    const double pn = sqrt(red[0]);
-    const double rz_n = red[1];
-    st->pnorm = pn;
-    st->beta = rz_n / st->rz;
-    st->rz = rz_n;
-    const int its = ++st->cg_its;
-    st->cg_active = (its < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < st->pnorm0 * P.cg_rel_tol);
+    if (P.slab) {
+      T.red[slot * 8] = red[0];
+      T.red[slot * 8 + 1] = red[1];
+    } else {
+      tail_cg_update(P, st, red[0], red[1]);
+    }
   }
 }
 
@@ -837,7 +879,8 @@ __global__ void __launch_bounds__(NT)
   const double *vars = T.vars_old[slot];
   const int e = blockIdx.x * NT + threadIdx.x;
   double red[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (e < P.nelem) {
+  // in a slab every element layer is summed by exactly one rank (the owner of its lower node plane)
+  if (e < P.nelem && e / (P.nex * P.ney) >= P.ez_own_lo && e / (P.nex * P.ney) < P.ez_own_hi) {
     const int ez = e / (P.nex * P.ney);
     const int r = e - ez * P.nex * P.ney;
     const int ey = r / P.nex, ex = r - ey * P.nex;
@@ -859,7 +902,12 @@ __global__ void __launch_bounds__(NT)
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
   if (grid_sum<6>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) T.stress[slot * 6 + q] = red[q] / 1.0;  // vol_tot = 1 (src/micropp.cpp:58)
+    for (int q = 0; q < 6; ++q) {
+      if (P.slab)
+        T.red[slot * 8 + q] = red[q];
+      else
+        T.stress[slot * 6 + q] = red[q] / 1.0;  // vol_tot = 1 (src/micropp.cpp:58)
+    }
   }
 }
 
@@ -901,6 +949,31 @@ __global__ void __launch_bounds__(NT)
     }
   }
   if (__syncthreads_or(nl) && threadIdx.x == 0) atomicOr(&st->nl_flag, 1);
+}
+
+// slab mode: scalar tails after the cross-rank all-reduce of T.red (kind: 0 rhs, 1 cg_init, 2 spmv, 3 cg_update,
+// 4 average stress)
+__global__ void k_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, int kind, int mode) {
+  const int slot = slot_of(L);
+  if (slot < 0 || threadIdx.x != 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  const double *red = T.red + slot * 8;
+  switch (kind) {
+    case 0:
+      if (mode == 1 && !st->nr_active) return;
+      tail_rhs(P, st, red[0], mode);
+      break;
+    case 1: tail_cg_init(P, st, red[0], red[1]); break;
+    case 2:
+      if (st->cg_active) tail_spmv(st, red[0]);
+      break;
+    case 3:
+      if (st->cg_active) tail_cg_update(P, st, red[0], red[1]);
+      break;
+    default:
+      for (int q = 0; q < 6; ++q) T.stress[slot * 6 + q] = red[q] / 1.0;
+      break;
+  }
 }
 
 __global__ void k_clear_nl(const int *__restrict__ list, int n, SlotTables T) {
@@ -1184,6 +1257,13 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   P.niz = std::max(P.nz - 2, 0);
   P.nint = P.nix * P.niy * P.niz;
   P.nint_pad = std::max((P.nint + 31) / 32 * 32, 32);
+  P.slab = cfg->slab;
+  P.koff = cfg->slab ? cfg->koff : 0;
+  P.nz_glob = cfg->slab ? cfg->nz_glob : P.nz;
+  P.halo_lo = cfg->slab ? cfg->halo_lo : 0;
+  P.halo_hi = cfg->slab ? cfg->halo_hi : 0;
+  P.ez_own_lo = cfg->slab ? cfg->ez_own_lo : 0;
+  P.ez_own_hi = cfg->slab ? cfg->ez_own_hi : std::max(P.nz - 1, 0);
   P.nex = P.nx - 1;
   P.ney = P.ny - 1;
   P.nez = P.nz - 1;
@@ -1323,6 +1403,8 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   CK(cudaMemset(T.eps, 0, sizeof(double) * 6 * W));
   CK(cudaMemset(T.stress, 0, sizeof(double) * 6 * W));
   CK(cudaMalloc(&T.partial, sizeof(double) * (size_t)NRED * nblk_max * W));
+  CK(cudaMalloc(&T.red, sizeof(double) * 8 * W));
+  CK(cudaMemset(T.red, 0, sizeof(double) * 8 * W));
   for (int l = 0; l < NLIST; ++l) CK(cudaMalloc(&c->d_list[l], sizeof(int) * W));
   CK(cudaMalloc(&c->d_count, sizeof(int)));
   CK(cudaMallocHost(&c->h_count, 4 * sizeof(int)));
@@ -1363,6 +1445,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   cudaFree(c->T.eps);
   cudaFree(c->T.stress);
   cudaFree(c->T.partial);
+  cudaFree(c->T.red);
   for (int l = 0; l < NLIST; ++l) cudaFree(c->d_list[l]);
   cudaFree(c->d_count);
   cudaFreeHost(c->h_count);
@@ -1730,6 +1813,20 @@ extern "C" int mgpu_newton_step_graph(mgpu_ctx *c, int n_active, int use_shared)
   c->launches += it->second.fixed_launches + (unsigned long long)it->second.body_launches * c->h_count[2];
   return c->h_count[0];
 }
+
+// ---- slab mode ---------------------------------------------------------------------------------
+extern "C" void mgpu_tail(mgpu_ctx *c, int l, int n, int kind, int mode) {
+  if (n <= 0) return;
+  c->launches++;
+  k_tail<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, kind, mode);
+  CK(cudaGetLastError());
+}
+extern "C" void *mgpu_dev_ptr(mgpu_ctx *c, int which) {
+  if (which == 10) return c->T.red;
+  if (which == 11) return c->T.stress;
+  return vec_of(c, which);
+}
+extern "C" void *mgpu_stream(mgpu_ctx *c) { return (void *)c->stream; }
 
 // ---- results ----------------------------------------------------------------------------------
 void mgpu_fetch_state(mgpu_ctx *c, int n, const int *slots, mgpu_slot_state *out) {

@@ -41,8 +41,10 @@ inline bool near2(double a, double ca, double b, double cb, double w) { return f
 
 }  // namespace
 
-template <>
-int micropp<3>::get_elem_type(int ex, int ey, int ez) const {
+// Free-function form (also used to classify the elements of one z-slab of a larger RVE): the unit cube
+// lx = ly = lz = 1 of src/micropp.cpp:46-48.
+int mpp_elem_type(int micro_type, const double *geo_params, double dx, double dy, double dz, int ex, int ey, int ez) {
+  const double lx = 1.0, ly = 1.0, lz = 1.0;
   const double p[3] = {ex * dx + dx / 2., ey * dy + dy / 2., ez * dz + dz / 2.};
   const double mid[3] = {lx / 2, ly / 2, lz / 2};
 
@@ -142,4 +144,9 @@ int micropp<3>::get_elem_type(int ex, int ey, int ez) const {
 
   cerr << "Invalid micro_type = " << micro_type << endl;
   return -1;
+}
+
+template <>
+int micropp<3>::get_elem_type(int ex, int ey, int ez) const {
+  return mpp_elem_type(micro_type, geo_params, dx, dy, dz, ex, ey, ez);
 }

@@ -20,15 +20,27 @@
 // ================================================================================================
 // construction
 // ================================================================================================
+int mpp_elem_type(int micro_type, const double *geo_params, double dx, double dy, double dz, int ex, int ey, int ez);
+
+namespace {
+void bmat_at(const double xg3[3], double dx, double dy, double dz, double b[6][24]);
+}
+
 template <>
 void micropp<3>::calc_bmat(int gp, double b[nvoi][npe * dim]) const {
+  bmat_at(xg[gp], dx, dy, dz, b);
+}
+
+namespace {
+void bmat_at(const double xg3[3], double dx, double dy, double dz, double b[6][24]) {
+  const int nvoi = 6, dim = 3;
   // Trilinear hex8 shape-function derivatives at Gauss point gp, scaled to the dx*dy*dz cell
   // (reference src/micro3D.cpp:81-120).  Node a sits at corner (cx,cy,cz) in {0,1}^3 with signs
   // s = 2c-1; dN_a/dx = sx (1 + sy eta)(1 + sz zeta)/8 * 2/dx.  Sign flips are exact, so the
   // products below round exactly like the reference's literal table.
   static const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
                                    {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
-  const double xi = xg[gp][0], eta = xg[gp][1], zeta = xg[gp][2];
+  const double xi = xg3[0], eta = xg3[1], zeta = xg3[2];
   for (int a = 0; a < 8; ++a) {
     const double sx = corner[a][0] ? 1.0 : -1.0, sy = corner[a][1] ? 1.0 : -1.0, sz = corner[a][2] ? 1.0 : -1.0;
     const double fx = 1 + sx * xi, fy = 1 + sy * eta, fz = 1 + sz * zeta;
@@ -48,8 +60,6 @@ void micropp<3>::calc_bmat(int gp, double b[nvoi][npe * dim]) const {
     b[5][a * dim + 2] = gy;
   }
 }
-
-namespace {
 
 // 24x24 element matrix of an elastic material on the uniform grid: sum over Gauss points of
 // B^T (C B wg), accumulated in the reference's loop order (src/assembly.cpp:141-178).
@@ -862,4 +872,80 @@ unsigned long long micropp3x_launch_count(const micropp3 *s) {
 double micropp3x_bench_spmv(micropp3 *s, int nslots, int iters) {
   return mgpu_bench_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters);
 }
+}
+
+// ================================================================================================
+// z-slab of one large RVE (BASELINE configs[4]: a single RVE split over several GPUs).  The reference has
+// no such mode; this builds the per-rank device context: local node planes [z0-halo, z1+halo)
+// of the global nx x ny x nz grid, with the global cell sizes, B matrices, element classification and
+// elastic element matrices.  The solver loop (halo exchange of p, all-reduce of the dot products) is driven
+// by the caller through include/mgpu.h -- see micropp_b200/slab.py.
+// ================================================================================================
+extern "C" mgpu_ctx *micropp3x_slab_create(const micropp3_params *q, int z0, int z1, int device) {
+  const int nx = q->size[0], ny = q->size[1], nzg = q->size[2];
+  if (z0 < 0 || z1 > nzg || z1 - z0 < 1) {
+    fprintf(stderr, "micropp-b200: bad slab [%d,%d) of %d planes\n", z0, z1, nzg);
+    abort();
+  }
+  const int halo_lo = z0 > 0 ? 1 : 0, halo_hi = z1 < nzg ? 1 : 0;
+  const int koff = z0 - halo_lo, nzl = (z1 + halo_hi) - koff;
+  const double dx = 1.0 / (nx - 1), dy = 1.0 / (ny - 1), dz = 1.0 / (nzg - 1);
+  const double wg = (dx * dy * dz) / 8;
+  const double g = CONSTXG;
+  const double xg[8][3] = {{-g, -g, -g}, {+g, -g, -g}, {+g, +g, -g}, {-g, +g, -g},
+                           {-g, -g, +g}, {+g, -g, +g}, {+g, +g, +g}, {-g, +g, +g}};
+  double bmat[8][6][24];
+  for (int gp = 0; gp < 8; ++gp) bmat_at(xg[gp], dx, dy, dz, bmat[gp]);
+
+  const int nex = nx - 1, ney = ny - 1, nezl = nzl - 1;
+  std::vector<int> et((size_t)std::max(nex * ney * nezl, 1), 0);
+  for (int ez = 0; ez < nezl; ++ez)
+    for (int ey = 0; ey < ney; ++ey)
+      for (int ex = 0; ex < nex; ++ex)
+        et[((size_t)ez * ney + ey) * nex + ex] = mpp_elem_type(q->type, q->geo_params, dx, dy, dz, ex, ey, ez + koff);
+
+  mgpu_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.nx = nx;
+  cfg.ny = ny;
+  cfg.nz = nzl;
+  cfg.device = device;
+  cfg.ngp = 0;
+  cfg.elem_type = et.data();
+  for (int gp = 0; gp < 8; ++gp)
+    for (int a = 0; a < 8; ++a) {
+      cfg.dsh[gp][a * 3 + 0] = bmat[gp][0][a * 3 + 0];
+      cfg.dsh[gp][a * 3 + 1] = bmat[gp][1][a * 3 + 1];
+      cfg.dsh[gp][a * 3 + 2] = bmat[gp][2][a * 3 + 2];
+    }
+  cfg.wg = wg;
+  cfg.dx = dx;
+  cfg.dy = dy;
+  cfg.dz = dz;
+  std::vector<double> ke(3 * 576, 0.0);
+  for (int i = 0; i < MAX_MATERIALS; ++i) {
+    material_base m;
+    material_set(&m, q->mat_type[i], q->mat_E[i], q->mat_nu[i], q->mat_Ka[i], q->mat_Sy[i], q->mat_Xt[i]);
+    const double vals[8] = {m.E, m.nu, m.Ka, m.Sy, m.k, m.mu, m.lambda, m.Xt};
+    memcpy(cfg.mat[i], vals, sizeof(vals));
+    cfg.mat_type[i] = m.type;
+    if (m.type == MATERIAL_ELASTIC) elastic_element_matrix(bmat, m, wg, &ke[i * 576]);
+  }
+  cfg.ke_elastic = ke.data();
+  cfg.nr_max_its = q->nr_max_its;
+  cfg.nr_max_tol = q->nr_max_tol;
+  cfg.nr_rel_tol = q->nr_rel_tol;
+  cfg.cg_max_its = CG_MAX_ITS;
+  cfg.cg_abs_tol = CG_ABS_TOL;
+  cfg.cg_rel_tol = CG_REL_TOL;
+  cfg.wave_cap = 1;
+  cfg.slab = 1;
+  cfg.koff = koff;
+  cfg.nz_glob = nzg;
+  cfg.halo_lo = halo_lo;
+  cfg.halo_hi = halo_hi;
+  // element layer e (global) is averaged by the rank that owns node plane e
+  cfg.ez_own_lo = z0 - koff;
+  cfg.ez_own_hi = std::min(z1, nzg - 1) - koff;
+  return mgpu_create(&cfg);
 }

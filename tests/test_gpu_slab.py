@@ -1,0 +1,63 @@
+"""-m gpu: one RVE split into z-slabs (BASELINE configs[4]).  On a single GPU the slabs live in one process and the
+halo exchange / all-reduce are device copies, which exercises the decomposition itself (ownership of planes and
+element layers, halo consistency, slab-local sums + scalar tails); the NCCL transport of the same code path is
+covered by tools/slab_bench.py under `gpurun --gpus N` and by tests/test_sharding.py (gloo) for the message pattern.
+
+Bar: the slab solution equals the single-domain solution of the same kernels to rounding (the only difference is the
+summation order of the dot products), iteration counts within +-1, stress within 1e-8 of the reference CPU path."""
+import numpy as np
+import pytest
+
+from common import CASES, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims,nslabs", [((10, 9, 12), 2), ((10, 9, 12), 3), ((12, 12, 12), 4), ((8, 8, 8), 1)])
+def test_slab_equals_single_domain(mpp, refpy, dims, nslabs):
+    from micropp_b200.slab import SlabRVE
+    kw = dict(size=dims, lin_stress=False, calc_ctan_lin=False, **CASES["elastic_sphere"])
+    eps = np.array([1.0e-3, -0.4e-3, 0.2e-3, 0.6e-3, -0.3e-3, 0.1e-3])
+    one = mpp.Micropp3(mpp.default_params(**kw))
+    one.set_strain(0, eps)
+    one.homogenize()
+    s1, c1 = one.get_stress(0), one.get_cost(0)
+    u1 = one.get_u(0, 1).reshape(-1, 3)
+
+    rve = SlabRVE(kw, nslabs=nslabs)
+    out = rve.homogenize(eps)
+    assert out["converged"] and abs(out["cg_its"] - c1) <= 1
+    assert relerr(out["stress"], s1) < 1e-10
+    assert relerr(rve.get_u(), u1) < 1e-8
+    assert rve.exchanges > 0 and rve.allreduces > 0
+    rve.close()
+
+    r = refpy.RefMicropp(refpy.default_params(**kw))
+    r.set_strain(0, eps)
+    r.homogenize()
+    assert relerr(out["stress"], r.get_stress(0)) < 1e-8
+    assert abs(out["cg_its"] - r.get_cost(0)) <= 1
+
+
+def test_slab_damage_first_step(mpp):
+    # history-free first load step of a damage RVE: tangents and residuals across the cuts
+    from micropp_b200.slab import SlabRVE
+    kw = dict(size=(9, 9, 11), lin_stress=False, calc_ctan_lin=False, nr_max_its=10, **CASES["damage_sphere"])
+    eps = np.array([0.012, 0, 0, 0, 0, 0.0])
+    one = mpp.Micropp3(mpp.default_params(**kw))
+    one.set_strain(0, eps)
+    one.homogenize()
+    rve = SlabRVE(kw, nslabs=3)
+    out = rve.homogenize(eps)
+    assert out["converged"] == one.has_converged(0)
+    assert abs(out["cg_its"] - one.get_cost(0)) <= out["newton_its"]
+    assert relerr(out["stress"], one.get_stress(0)) < 1e-8
+    rve.close()
+
+
+def test_plane_ranges():
+    from micropp_b200.slab import plane_range
+    for nz in (8, 50, 200):
+        for r in (1, 2, 3, 4, 8):
+            rr = [plane_range(nz, r, s) for s in range(r)]
+            assert rr[0][0] == 0 and rr[-1][1] == nz and all(a[1] == b[0] for a, b in zip(rr[:-1], rr[1:]))

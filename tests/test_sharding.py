@@ -69,3 +69,34 @@ def test_two_rank_sharding_matches_serial(tmp_path):
     m.homogenize()
     want = np.array([m.get_stress(g) for g in range(ngp)])
     assert np.array_equal(got, want)  # GP independence: bit-identical however the batch is split
+
+
+def _halo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from micropp_b200.slab import exchange_planes, plane_range
+    nz, plane = 7, 5
+    z0, z1 = plane_range(nz, world, rank)
+    glob = torch.arange(nz * plane, dtype=torch.float64).view(nz, plane)   # the "p" every rank should agree on
+    lo, hi = int(rank > 0), int(rank + 1 < world)
+    local = torch.full((z1 - z0 + lo + hi, plane), -1.0, dtype=torch.float64)
+    local[lo:lo + z1 - z0] = glob[z0:z1]                                      # owned planes only
+    rlo, rhi = torch.empty(plane, dtype=torch.float64), torch.empty(plane, dtype=torch.float64)
+    exchange_planes(dist, rank, world, local[lo].clone(), local[lo + z1 - z0 - 1].clone(), rlo, rhi)
+    if lo:
+        local[0] = rlo
+    if hi:
+        local[-1] = rhi
+    ok = torch.equal(local, glob[z0 - lo:z1 + hi])
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "halo_ok.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_pattern_gloo(tmp_path, world):
+    port = 31000 + (os.getpid() % 2000) + world
+    mp.spawn(_halo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / "halo_ok.npy")[0] == 1.0
