@@ -68,6 +68,9 @@ typedef struct mgpu_config {
      local plane k is global plane k + koff of nz_glob; halo_lo/halo_hi: the first/last local plane belongs to the
      neighbour rank; element layers [ez_own_lo, ez_own_hi) (local numbering) are the ones this rank averages. */
   int slab, koff, nz_glob, halo_lo, halo_hi, ez_own_lo, ez_own_hi;
+  /* all-elastic RVEs only: serve the Jacobian from the table of distinct ELL row blocks (no per-slot matrix, DPCG
+     operator 3) instead of assembling one matrix per slot; ignored when a damage/plastic material is in use */
+  int implicit_elastic;
 } mgpu_config;
 
 /* ---- context ---- */
@@ -104,6 +107,11 @@ void mgpu_zero_u(mgpu_ctx *, int which_list, int n);                /* u_slot <-
 void mgpu_set_bc(mgpu_ctx *, int which_list, int n);
 void mgpu_asm_rhs(mgpu_ctx *, int which_list, int n, int mode);     /* mode 0: first of a Newton solve, 1: after update, 2: plain */
 void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_shared: assemble slot list[0] into the shared A0 buffer */
+/* use_shared selects the operator of the solve: 0 the slot's own matrix, 1 the shared A0, 2 the generic host matrix,
+   3 the implicit operator of an all-elastic RVE (mgpu_implicit() != 0); mgpu_cg_update/pupdate follow the operator
+   of the last mgpu_cg_init */
+int mgpu_implicit(const mgpu_ctx *);
+int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
 void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitrary matrix: boundary rows read too */

@@ -50,6 +50,8 @@ void micropp3_get_ctans(const struct micropp3 *self, double *ctan);
 int micropp3x_nelem(const struct micropp3 *self);
 int micropp3x_nndim(const struct micropp3 *self);
 int micropp3x_wave_size(const struct micropp3 *self);
+/* distinct ELL row blocks of the implicit operator of an all-elastic RVE; 0 = one assembled matrix per slot */
+int micropp3x_implicit_rows(const struct micropp3 *self);
 void micropp3x_get_elem_type(const struct micropp3 *self, int *out);
 void micropp3x_get_bmat(const struct micropp3 *self, double *out /* [8][6][24] */);
 void micropp3x_get_ctan_lin(const struct micropp3 *self, double *out36);

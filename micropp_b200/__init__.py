@@ -97,7 +97,7 @@ def load():
         "micropp3_get_ctans": (None, [H, _dp]),
         "micropp3x_nelem": (C.c_int, [H]),
         "micropp3x_nndim": (C.c_int, [H]),
-        "micropp3x_wave_size": (C.c_int, [H]),
+        "micropp3x_wave_size": (C.c_int, [H]), "micropp3x_implicit_rows": (C.c_int, [H]),
         "micropp3x_get_elem_type": (None, [H, _ip]),
         "micropp3x_get_bmat": (None, [H, _dp]),
         "micropp3x_get_ctan_lin": (None, [H, _dp]),
@@ -269,6 +269,9 @@ class Micropp3:
     # ---- inspection -----------------------------------------------------------------------------
     def wave_size(self):
         return int(self.lib.micropp3x_wave_size(C.byref(self.h)))
+
+    def implicit_rows(self):
+        return int(self.lib.micropp3x_implicit_rows(C.byref(self.h)))
 
     def elem_type(self):
         out = np.zeros(max(self.nelem, 1), dtype=np.int32)

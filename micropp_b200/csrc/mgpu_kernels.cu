@@ -77,8 +77,16 @@ struct VecPool {
   double *mat;                              // [W][243*nint_pad], interior rows, 32-node tiles
   double *mat_shared;                       // [243*nint_pad] (A0)
   double *gen;                              // [3*nn][81] host matrix of the generic ELL API (reference layout)
+  // implicit operator of an all-elastic RVE: the ELL row block of an interior node is a pure function of the
+  // materials of its 8 elements, so only the DISTINCT row blocks are kept (rows[id][243]) plus one id per node
+  const double *rows;                       // [nrows][243]
+  const double *rkinv;                      // [nrows][3]  1 / diagonal (the Jacobi preconditioner, src/ell.cpp:73-76)
+  const int *rowid;                         // [nint_pad]
   size_t vstride, mstride;
 };
+
+// operator selector of the DPCG kernels
+enum { OP_SLOT = 0, OP_SHARED = 1, OP_GENERIC = 2, OP_IMPLICIT = 3 };
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -441,27 +449,28 @@ __device__ __forceinline__ void gather_block_elastic(const double *__restrict__ 
   }
 }
 
+// value of plane q goes to A[q * stride] (A already points at the node's first plane)
 template <int NBR>
 __device__ __forceinline__ void asm_elastic_slot(const double *__restrict__ s_ke, const int (&et)[8], double *A,
-                                                 size_t nn_pad, int n) {
+                                                 int stride) {
   constexpr int DI = NBR % 3 - 1, DJ = (NBR / 3) % 3 - 1, DK = NBR / 9 - 1;
   double acc[9];
   gather_block_elastic<DI, DJ, DK>(s_ke, et, acc);
 #pragma unroll
-  for (int q = 0; q < 9; ++q) A[aidx(NBR * 9 + q, n)] = acc[q];
+  for (int q = 0; q < 9; ++q) A[(size_t)(NBR * 9 + q) * stride] = acc[q];
 }
 
 template <int NBR>
 struct AsmElasticLoop {
   static __device__ __forceinline__ void run(const double *__restrict__ s_ke, const int (&et)[8], double *A,
-                                             size_t nn_pad, int n) {
-    asm_elastic_slot<NBR>(s_ke, et, A, nn_pad, n);
-    AsmElasticLoop<NBR + 1>::run(s_ke, et, A, nn_pad, n);
+                                             int stride) {
+    asm_elastic_slot<NBR>(s_ke, et, A, stride);
+    AsmElasticLoop<NBR + 1>::run(s_ke, et, A, stride);
   }
 };
 template <>
 struct AsmElasticLoop<27> {
-  static __device__ __forceinline__ void run(const double *__restrict__, const int (&)[8], double *, size_t, int) {}
+  static __device__ __forceinline__ void run(const double *__restrict__, const int (&)[8], double *, int) {}
 };
 
 __global__ void __launch_bounds__(NT)
@@ -484,7 +493,30 @@ __global__ void __launch_bounds__(NT)
     const int ex = i - 1 + ((c >> 2) & 1), ey = j - 1 + ((c >> 1) & 1), ez = k - 1 + (c & 1);
     et[c] = __ldg(&elem_type[(ez * P.ney + ey) * P.nex + ex]);
   }
-  AsmElasticLoop<0>::run(s_ke, et, A, (size_t)P.nint_pad, m);
+  AsmElasticLoop<0>::run(s_ke, et, A + aidx(0, m), 32);
+}
+
+// Distinct row blocks of the implicit elastic operator: thread per row id; `codes[id]` = sum_c type_c * 3^c over the
+// 8 elements around a node (c as in k_asm_mat_elastic), the row block is gathered by the SAME code as the explicit
+// assembly, so the implicit operator is bit-identical to the assembled one.
+__global__ void __launch_bounds__(NT)
+    k_rows_build(const int *__restrict__ codes, int nrows, double *rows, double *rkinv,
+                 const double *__restrict__ ke_tab) {
+  __shared__ double s_ke[3 * 576];
+  for (int q = threadIdx.x; q < 3 * 576; q += NT) s_ke[q] = ke_tab[q];
+  __syncthreads();
+  const int id = blockIdx.x * NT + threadIdx.x;
+  if (id >= nrows) return;
+  int code = codes[id];
+  int et[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    et[c] = code % 3;
+    code /= 3;
+  }
+  AsmElasticLoop<0>::run(s_ke, et, rows + (size_t)id * NPLANE, 1);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) rkinv[id * 3 + d] = 1 / rows[(size_t)id * NPLANE + 13 * 9 + d * 4];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,7 +670,7 @@ __global__ void __launch_bounds__(NT)
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   // use_shared: 0 per-slot matrix, 1 the shared linear matrix (A0), 2 the generic host matrix (reference layout)
-  const double *A = use_shared == 1 ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
+  const double *A = use_shared == OP_SHARED ? V.mat_shared : V.mat + (size_t)slot * V.mstride;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   double red[2] = {0.0, 0.0};
@@ -651,17 +683,20 @@ __global__ void __launch_bounds__(NT)
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
       double diag = 1.0;  // boundary rows are identity rows (ell_set_bc_3D)
-      if (use_shared == 2)
+      if (use_shared == OP_GENERIC)
         diag = V.gen[((size_t)n * 3 + d) * 81 + 13 * 3 + d];
-      else if (!bnd)
+      else if (use_shared != OP_IMPLICIT && !bnd)
         diag = A[aidx(13 * 9 + d * 4, m)];
-      const double kk = 1 / diag;  // src/ell.cpp:73-76
+      // src/ell.cpp:73-76 (the implicit operator keeps 1/diag per distinct row block)
+      const double kk = (use_shared == OP_IMPLICIT && !bnd) ? __ldg(&V.rkinv[__ldg(&V.rowid[m]) * 3 + d]) : 1 / diag;
       const double r = V.b[ix];    // r = b - A*0 (src/ell.cpp:78-82)
       const double z = kk * r;
-      V.k[ix] = kk;
+      if (use_shared != OP_IMPLICIT) {  // the implicit operator re-derives k (and z = k r) from its row table
+        V.k[ix] = kk;
+        V.z[ix] = z;
+      }
       V.du[ix] = 0.0;
       V.r[ix] = r;
-      V.z[ix] = z;
       V.p[ix] = z;
       V.Ap[ix] = 0.0;  // boundary entries of Ap are never written by the SpMV (p is 0 there)
       red[0] += r * z;
@@ -745,6 +780,190 @@ __global__ void __launch_bounds__(NT)
       T.red[slot * 8] = red[0];
     else
       tail_spmv(st, red[0]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Implicit operator of an all-elastic RVE (every material elastic => the Jacobian does not depend on u,
+// src/material.cpp:84-94, and is the same for every macro Gauss point and every Newton step).  No matrix is
+// stored per RVE: a thread owns one interior node, fetches the node's row block from the small table of distinct
+// row blocks (L1-resident: almost every node of a warp uses the same block, so the 243 loads are broadcasts) and
+// applies it to MR right-hand sides (slots) at once.  Per RVE the kernel moves 48 B/node (p in, Ap out) instead
+// of 1992 B/node; the FMA order per slot is exactly that of k_spmv_dot, so results are bit-identical to the
+// assembled path.
+// ------------------------------------------------------------------------------------------------
+constexpr int MR = 8;  // right-hand sides per thread
+
+// blockIdx.y = group of R consecutive entries of the slot list (n_list entries; inside a graph the device-side count)
+template <int R>
+__global__ void __launch_bounds__(NT, 3)
+    k_spmv_dot_imp(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V, int force) {
+  __shared__ double sm[R * (NT / 32)];
+  __shared__ int s_slot[R];
+  __shared__ int s_last[R];
+  if (threadIdx.x < R) {
+    const int yy = (int)blockIdx.y * R + (int)threadIdx.x + L.yoff;
+    const int cnt = L.dcount ? min(*L.dcount, n_list + L.yoff) : n_list + L.yoff;
+    int slot = yy < cnt ? L.list[yy] : -1;
+    if (slot >= 0 && !force && !T.state[slot].cg_active) slot = -1;
+    s_slot[threadIdx.x] = slot;
+  }
+  __syncthreads();
+  int any = -1;
+#pragma unroll
+  for (int r = R - 1; r >= 0; --r)
+    if (s_slot[r] >= 0) any = s_slot[r];
+  if (any < 0) return;
+  unsigned off[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) off[r] = (unsigned)((size_t)(s_slot[r] >= 0 ? s_slot[r] : any) * V.vstride);
+
+  const int m = blockIdx.x * NT + threadIdx.x;
+  double red[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) red[r] = 0.0;
+  if (m < P.nint) {
+    int i, j, k;
+    const int n = interior_node(P, m, i, j, k);
+    const size_t npad = P.nn_pad;
+    double y[R][3];
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[r][0] = y[r][1] = y[r][2] = 0.0;
+    const double *a = V.rows + (size_t)__ldg(&V.rowid[m]) * NPLANE;
+    // rolled over the 9 (dz, dy) neighbour rows, unrolled over dx: bounds the loads the scheduler can hoist
+#pragma unroll 1
+    for (int row = 0; row < 9; ++row) {
+      const int dk = row / 3 - 1, dj = row - (dk + 1) * 3 - 1;
+      const int q0 = n + dj * P.nx + dk * P.nxny;
+      const double *ar = a + row * 27;
+#pragma unroll
+      for (int di = -1; di <= 1; ++di) {
+        double av[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) av[t] = __ldg(ar + (di + 1) * 9 + t);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double *pp = V.p + ((size_t)off[r] + (q0 + di));
+          const double px = pp[0], py = pp[npad], pz = pp[2 * npad];
+          y[r][0] += av[0] * px;
+          y[r][0] += av[1] * py;
+          y[r][0] += av[2] * pz;
+          y[r][1] += av[3] * px;
+          y[r][1] += av[4] * py;
+          y[r][1] += av[5] * pz;
+          y[r][2] += av[6] * px;
+          y[r][2] += av[7] * py;
+          y[r][2] += av[8] * pz;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (s_slot[r] >= 0) {
+        const double *pp = V.p + ((size_t)off[r] + n);
+        double *Ap = V.Ap + ((size_t)off[r] + n);
+        Ap[0] = y[r][0];
+        Ap[npad] = y[r][1];
+        Ap[2 * npad] = y[r][2];
+        red[r] = pp[0] * y[r][0] + pp[npad] * y[r][1] + pp[2 * npad] * y[r][2];
+      }
+    }
+  }
+  // per-slot deterministic ticket reductions (the same partial layout and summation order as grid_sum<1>)
+  block_sum<R>(red, sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (s_slot[r] >= 0) T.partial[(size_t)s_slot[r] * NRED * T.nblk_max + blockIdx.x] = red[r];
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int last = 0;
+      if (s_slot[r] >= 0) last = atomicAdd(&T.state[s_slot[r]].ticket, 1u) == gridDim.x - 1;
+      s_last[r] = last;
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < R; ++r) {
+    if (!s_last[r]) continue;
+    __threadfence();
+    const int slot = s_slot[r];
+    const double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+    double acc[1] = {0.0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) acc[0] += __ldcg(&partial[b]);
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) {
+      T.state[slot].ticket = 0u;
+      if (P.slab)
+        T.red[slot * 8] = acc[0];
+      else
+        tail_spmv(&T.state[slot], acc[0]);
+    }
+  }
+}
+
+__device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, int n, int d) {
+  int i, j, k;
+  node_ijk(P, n, i, j, k);
+  if (on_boundary(P, i, j, k)) return 1.0;  // 1 / 1
+  const int m = interior_index(P, i, j, k);
+  return __ldg(&V.rkinv[__ldg(&V.rowid[m]) * 3 + d]);
+}
+
+// cg_update / cg_pupdate of the implicit operator: k = 1/diag comes from the row table and z = k r is recomputed
+// instead of being stored (the same multiplication => the same bits); 144 + 72 B/node instead of 192 + 72.
+__global__ void __launch_bounds__(NT)
+    k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!st->cg_active) return;
+  const double alpha = st->alpha;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double red[2] = {0.0, 0.0};
+  if (n < P.nn) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t ix = vo + (size_t)d * P.nn_pad + n;
+      const double pp = V.p[ix];
+      V.du[ix] += alpha * pp;
+      const double r = V.r[ix] - alpha * V.Ap[ix];
+      V.r[ix] = r;
+      const double z = __dmul_rn(imp_kk(P, V, n, d), r);  // rounded product, as when z is stored (k_cg_update)
+      red[0] += z * z;
+      red[1] += r * z;
+    }
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
+    if (P.slab) {
+      T.red[slot * 8] = red[0];
+      T.red[slot * 8 + 1] = red[1];
+    } else {
+      tail_cg_update(P, st, red[0], red[1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+    k_cg_pupdate_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  const mgpu_slot_state *st = &T.state[slot];
+  if (!st->cg_active) return;
+  const double beta = st->beta;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= P.nn) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const size_t ix = vo + (size_t)d * P.nn_pad + n;
+    const double z = __dmul_rn(imp_kk(P, V, n, d), V.r[ix]);  // never fused into the FMA below
+    V.p[ix] = z + beta * V.p[ix];
   }
 }
 
@@ -1056,6 +1275,10 @@ struct mgpu_ctx {
   MeshConst mc;
   int ngp = 0, W = 0;
   bool all_elastic = true;
+  bool implicit = false;  // all-elastic RVE served by the implicit operator (no per-slot matrices)
+  int mat_slots = 0;      // slots of the explicit matrix pool
+  int cg_op = OP_SLOT;    // operator of the DPCG solve in flight (set by mgpu_cg_init)
+  int nrows = 0;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
   double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
@@ -1096,7 +1319,7 @@ struct mgpu_ctx {
     cudaGraphExec_t exec;
     int fixed_launches, body_launches;
   };
-  std::map<long long, StepGraph> step_graphs;  // key = bucket * 2 + use_shared
+  std::map<long long, StepGraph> step_graphs;  // key = bucket * 4 + operator
 };
 
 namespace {
@@ -1337,10 +1560,12 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   // wave size from the HBM left after reserving room for internal variables of every GP
   const size_t mlen = (size_t)NPLANE * P.nint_pad;
   const int nblk_max = std::max((P.nn + NT - 1) / NT, (P.nelem + NT - 1) / NT);
-  const size_t per_slot = sizeof(double) * (mlen + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256;
+  c->implicit = c->all_elastic && cfg->implicit_elastic && P.nint > 0;
+  const size_t per_slot =
+      sizeof(double) * ((c->implicit ? 0 : mlen) + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  size_t reserve = sizeof(double) * mlen /* A0 */ + (size_t(1) << 30);
+  size_t reserve = sizeof(double) * mlen * (c->implicit ? 3 : 1) /* A0 (+ 2 explicit slots) */ + (size_t(1) << 30);
   const size_t ctan_per_slot = sizeof(double) * CTAN_LEN * (size_t)P.nelem_pad;
   const size_t be_per_slot = sizeof(double) * 24 * (size_t)P.nelem_pad;
   {
@@ -1379,16 +1604,56 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     CK(cudaMalloc(pp, sizeof(double) * vlen * W));
     CK(cudaMemset(*pp, 0, sizeof(double) * vlen * W));
   }
-  CK(cudaMalloc(&V.mat, sizeof(double) * mlen * W));
+  // explicit matrices: one per slot, or just two (host-pointer API, debugging) next to the implicit operator
+  c->mat_slots = c->implicit ? (int)std::min<long long>(W, 2) : (int)W;
+  CK(cudaMalloc(&V.mat, sizeof(double) * mlen * c->mat_slots));
   c->be_chunk = std::min(c->be_chunk, (int)W);
   CK(cudaMalloc(&c->d_be, be_per_slot * c->be_chunk));
   if (!c->all_elastic) {
     c->ctan_chunk = std::min(c->ctan_chunk, (int)W);
     CK(cudaMalloc(&c->d_ctan, ctan_per_slot * c->ctan_chunk));
   }
-  CK(cudaMemsetAsync(V.mat, 0, sizeof(double) * mlen * W, c->stream));  // tile padding stays defined
+  CK(cudaMemsetAsync(V.mat, 0, sizeof(double) * mlen * c->mat_slots, c->stream));  // tile padding stays defined
   V.mat_shared = nullptr;  // allocated on first use (use_A0)
   V.gen = nullptr;         // allocated on first use (generic host-matrix API)
+
+  if (c->implicit) {
+    // distinct row blocks: code = sum_c type_c 3^c over the 8 elements around an interior node
+    std::vector<int> code2id(6561, -1), codes, rowid(P.nint_pad, 0);
+    for (int m = 0; m < P.nint; ++m) {
+      const int pl = P.nix * P.niy;
+      const int kk = m / pl, r = m - kk * pl, jj = r / P.nix, ii = r - jj * P.nix;
+      const int i = ii + 1, j = jj + 1, k = kk + 1;
+      int code = 0, w3 = 1;
+      for (int cc = 0; cc < 8; ++cc) {
+        const int ex = i - 1 + ((cc >> 2) & 1), ey = j - 1 + ((cc >> 1) & 1), ez = k - 1 + (cc & 1);
+        code += w3 * cfg->elem_type[(ez * P.ney + ey) * P.nex + ex];
+        w3 *= 3;
+      }
+      if (code2id[code] < 0) {
+        code2id[code] = (int)codes.size();
+        codes.push_back(code);
+      }
+      rowid[m] = code2id[code];
+    }
+    c->nrows = (int)codes.size();
+    int *d_codes = nullptr, *d_rowid = nullptr;
+    double *d_rows = nullptr, *d_rkinv = nullptr;
+    CK(cudaMalloc(&d_codes, sizeof(int) * c->nrows));
+    CK(cudaMalloc(&d_rowid, sizeof(int) * P.nint_pad));
+    CK(cudaMalloc(&d_rows, sizeof(double) * NPLANE * c->nrows));
+    CK(cudaMalloc(&d_rkinv, sizeof(double) * 3 * c->nrows));
+    CK(cudaMemcpy(d_codes, codes.data(), sizeof(int) * c->nrows, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_rowid, rowid.data(), sizeof(int) * P.nint_pad, cudaMemcpyHostToDevice));
+    k_rows_build<<<(c->nrows + NT - 1) / NT, NT, 0, c->stream>>>(d_codes, c->nrows, d_rows, d_rkinv, c->d_ke);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(d_codes));
+    c->launches++;
+    V.rows = d_rows;
+    V.rkinv = d_rkinv;
+    V.rowid = d_rowid;
+  }
 
   SlotTables &T = c->T;
   T.nblk_max = nblk_max;
@@ -1437,6 +1702,9 @@ void mgpu_destroy(mgpu_ctx *c) {
   for (auto p : vecs) cudaFree(p);
   if (c->V.mat_shared) cudaFree(c->V.mat_shared);
   if (c->V.gen) cudaFree(c->V.gen);
+  if (c->V.rows) cudaFree((void *)c->V.rows);
+  if (c->V.rkinv) cudaFree((void *)c->V.rkinv);
+  if (c->V.rowid) cudaFree((void *)c->V.rowid);
   cudaFree(c->T.state);
   cudaFree((void *)c->T.vars_old);
   cudaFree((void *)c->T.vars_new);
@@ -1625,6 +1893,11 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
     shared = c->V.mat_shared;
     n = 1;
   }
+  if (!to_shared && n > c->mat_slots) {
+    fprintf(stderr, "micropp-b200: explicit assembly of %d slots, but the matrix pool holds %d (implicit operator)\n",
+            n, c->mat_slots);
+    abort();
+  }
   ProfScope ps(c, 1, n);
   if (c->all_elastic) {
     k_asm_mat_elastic<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->V.mat, c->V.mstride, shared,
@@ -1644,8 +1917,16 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
   }
   CK(cudaGetLastError());
 }
+int mgpu_implicit(const mgpu_ctx *c) { return c->implicit ? 1 : 0; }
+int mgpu_implicit_rows(const mgpu_ctx *c) { return c->nrows; }
+
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
+  if (use_shared == OP_IMPLICIT && !c->implicit) {
+    fprintf(stderr, "micropp-b200: implicit operator requested for an RVE that is not all-elastic\n");
+    abort();
+  }
+  c->cg_op = use_shared;
   ProfScope ps(c, 3, n);
   k_cg_init<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared);
   CK(cudaGetLastError());
@@ -1653,19 +1934,29 @@ void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
 void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
-  k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
+  if (use_shared == OP_IMPLICIT) {
+    k_spmv_dot_imp<MR><<<int_grid(c, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, 0);
+  } else {
+    k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
+  }
   CK(cudaGetLastError());
 }
 void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
-  k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  if (c->cg_op == OP_IMPLICIT)
+    k_cg_update_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  else
+    k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
-  k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  if (c->cg_op == OP_IMPLICIT)
+    k_cg_pupdate_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  else
+    k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
@@ -1743,7 +2034,7 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
   // head: Jacobian, CG start, CG list := Newton-list slots whose loop-head test says "iterate"
   capture_begin(c, g, nullptr, 0);
   c->dyn_count = c->d_cnt2;
-  if (!use_shared) mgpu_asm_mat(c, 1, B, 0);
+  if (use_shared == OP_SLOT) mgpu_asm_mat(c, 1, B, 0);
   mgpu_cg_init(c, 1, B, use_shared);
   k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[2], c->d_cnt2 + 1, nullptr, c->T, 1, cond,
                                        1, nullptr);
@@ -1804,7 +2095,7 @@ extern "C" int mgpu_newton_step_graph(mgpu_ctx *c, int n_active, int use_shared)
   int B = 1;
   while (B < n_active) B <<= 1;
   B = std::min(B, c->W);
-  const long long key = (long long)B * 2 + (use_shared ? 1 : 0);
+  const long long key = (long long)B * 4 + use_shared;
   auto it = c->step_graphs.find(key);
   if (it == c->step_graphs.end()) it = c->step_graphs.emplace(key, build_step_graph(c, B, use_shared)).first;
   CK(cudaMemsetAsync(c->d_cnt2 + 2, 0, sizeof(int), c->stream));

@@ -191,10 +191,14 @@ micropp<3>::micropp(const micropp_params_t &params)
   cfg.cg_abs_tol = CG_ABS_TOL;
   cfg.cg_rel_tol = CG_REL_TOL;
   cfg.wave_cap = 0;
+  // all-elastic RVEs run DPCG on the implicit operator (MICROPP_IMPLICIT=0: one assembled ELL matrix per slot)
+  cfg.implicit_elastic = 1;
+  if (const char *env = getenv("MICROPP_IMPLICIT")) cfg.implicit_elastic = atoi(env) != 0;
 
   engine = new mpp_engine();
   engine->ctx = mgpu_create(&cfg);
   engine->W = mgpu_wave_size(engine->ctx);
+  engine->implicit = mgpu_implicit(engine->ctx) != 0;
   engine->use_A0 = use_A0;
   engine->its_with_A0 = its_with_A0;
   if (const char *env = getenv("MICROPP_CG_CHUNK")) engine->cg_chunk = std::max(1, atoi(env));
@@ -707,7 +711,11 @@ newton_t micropp<3>::newton_raphson(ell_matrix *A, double *b, double *u, double 
   mgpu_stage_get_u(engine->ctx, kSlot0, u);
   if (b) mgpu_stage_get_vec(engine->ctx, kSlot0, 0, b);
   if (du) mgpu_stage_get_vec(engine->ctx, kSlot0, 1, du);
-  if (A && A->vals && res[0].its > 0) mgpu_stage_get_mat(engine->ctx, kSlot0, A->vals);
+  if (A && A->vals && res[0].its > 0) {
+    // the implicit operator never materialises the Jacobian: assemble it for the caller who asked to see it
+    if (engine->implicit) mgpu_asm_mat(engine->ctx, mpp_engine::L_SUB, 1, 0);
+    mgpu_stage_get_mat(engine->ctx, kSlot0, A->vals);
+  }
   return res[0];
 }
 
@@ -792,6 +800,10 @@ extern "C" {
 int micropp3x_nelem(const micropp3 *s) { return mpp_access::nelem((micropp<3> *)s->ptr); }
 int micropp3x_nndim(const micropp3 *s) { return mpp_access::nndim((micropp<3> *)s->ptr); }
 int micropp3x_wave_size(const micropp3 *s) { return mpp_access::engine((micropp<3> *)s->ptr)->W; }
+int micropp3x_implicit_rows(const micropp3 *s) {
+  mpp_engine *e = mpp_access::engine((micropp<3> *)s->ptr);
+  return e->implicit ? mgpu_implicit_rows(e->ctx) : 0;
+}
 void micropp3x_get_elem_type(const micropp3 *s, int *out) {
   const micropp<3> *m = (micropp<3> *)s->ptr;
   memcpy(out, mpp_access::elem_type(m), sizeof(int) * mpp_access::nelem(m));
@@ -939,6 +951,8 @@ extern "C" mgpu_ctx *micropp3x_slab_create(const micropp3_params *q, int z0, int
   cfg.cg_abs_tol = CG_ABS_TOL;
   cfg.cg_rel_tol = CG_REL_TOL;
   cfg.wave_cap = 1;
+  cfg.implicit_elastic = 1;
+  if (const char *env = getenv("MICROPP_IMPLICIT")) cfg.implicit_elastic = atoi(env) != 0;
   cfg.slab = 1;
   cfg.koff = koff;
   cfg.nz_glob = nzg;

@@ -14,6 +14,7 @@ struct mpp_engine {
   bool use_A0 = false;
   int its_with_A0 = 1;
   bool A0_ready = false;
+  bool implicit = false;  // all-elastic RVE: DPCG on the implicit operator (mgpu_implicit), no Jacobian assembly
   int cg_chunk = 8;
   bool use_graphs = true;  // one CUDA graph per Newton step (MICROPP_GRAPHS=0: plain stream launches)
   bool profiling = false;  // per-kernel CUDA-event timing needs plain launches
@@ -52,11 +53,14 @@ struct mpp_engine {
       const int na = mgpu_compact(ctx, list, n, L_NEWTON, 0);
       if (na == 0) break;
       // linear Jacobian for the first its_with_A0 iterations (src/solve.cpp:56-66)
-      const int shared = (use_A0 && A0_ready && it <= its_with_A0 - 1) ? 1 : 0;
+      // an all-elastic Jacobian does not depend on u (src/material.cpp:84-94): the implicit operator IS the
+      // matrix assembly_mat would build, for every slot and every step (which also covers the A0 shortcut)
+      auto op_of = [&](int step) { return implicit ? 3 : ((use_A0 && A0_ready && step <= its_with_A0 - 1) ? 1 : 0); };
+      const int shared = op_of(it);
       if (use_graphs && !profiling) {
         int left = na;
         while (left > 0) {  // every graph launch is one Newton step of all still-active slots
-          left = mgpu_newton_step_graph(ctx, left, (use_A0 && A0_ready && it <= its_with_A0 - 1) ? 1 : 0);
+          left = mgpu_newton_step_graph(ctx, left, op_of(it));
           ++it;
         }
         break;

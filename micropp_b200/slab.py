@@ -86,7 +86,7 @@ def _bind(lib):
         "mgpu_tail": (None, [V, C.c_int, C.c_int, C.c_int, C.c_int]),
         "mgpu_fetch_state": (None, [V, C.c_int, _ip, C.POINTER(SlotState)]),
         "mgpu_fetch_stress": (None, [V, C.c_int, _ip, _dp]),
-        "mgpu_dev_ptr": (V, [V, C.c_int]), "mgpu_stream": (V, [V]),
+        "mgpu_dev_ptr": (V, [V, C.c_int]), "mgpu_stream": (V, [V]), "mgpu_implicit": (C.c_int, [V]),
         "mgpu_stage_get_u": (None, [V, C.c_int, _dp]),
     }
     for name, (res, args) in sig.items():
@@ -176,6 +176,8 @@ class SlabRVE:
             self.rbuf = [torch.empty(n3, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.exchanges = 0
         self.allreduces = 0
+        # DPCG operator: 3 = implicit operator of an all-elastic RVE (no assembled matrix), 0 = the slab's own ELL matrix
+        self.op = 3 if all(self.lib.mgpu_implicit(s.ctx) for s in self.slabs) else 0
 
     # ------------------------------------------------------------------ communication
     def _allreduce(self, k: int):
@@ -231,11 +233,11 @@ class SlabRVE:
     # ------------------------------------------------------------------ solver
     def cg_solve(self):
         lib, L0 = self.lib, self.L0
-        self._reduced(lib.mgpu_cg_init, (L0, 1, 0), 2, 1)
+        self._reduced(lib.mgpu_cg_init, (L0, 1, self.op), 2, 1)
         while self.slabs[0].state().cg_active:
             for _ in range(self.cg_chunk):
                 self._exchange_p()
-                self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, 0), 1, 2)
+                self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, self.op), 1, 2)
                 self._reduced(lib.mgpu_cg_update, (L0, 1), 2, 3)
                 self._each(lib.mgpu_cg_pupdate, L0, 1)
 
@@ -249,7 +251,8 @@ class SlabRVE:
         self._each(lib.mgpu_set_bc, L0, 1)
         self._reduced(lib.mgpu_asm_rhs, (L0, 1, 0), 1, 0, 0)
         while self.slabs[0].state().nr_active:
-            self._each(lib.mgpu_asm_mat, L0, 1, 0)
+            if self.op == 0:
+                self._each(lib.mgpu_asm_mat, L0, 1, 0)
             self.cg_solve()
             self._each(lib.mgpu_axpy_u, L0, 1)
             self._reduced(lib.mgpu_asm_rhs, (L0, 1, 1), 1, 0, 1)
