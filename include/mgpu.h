@@ -112,9 +112,13 @@ void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_share
    of the last mgpu_cg_init */
 int mgpu_implicit(const mgpu_ctx *);
 int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
+int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 simple, 1 tiled (cp.async), 2 tiled (TMA) */
 void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitrary matrix: boundary rows read too */
+/* one forced application Ap = A p (+ p.Ap in the slot state) for kernel parity tests; op as in mgpu_cg_init;
+   imp_kernel: -1 the context's choice, 0 the simple multi-right-hand-side kernel, 1 the shared-memory tiled kernel */
+void mgpu_apply_operator(mgpu_ctx *, int which_list, int n, int op, int imp_kernel);
 void mgpu_cg_update(mgpu_ctx *, int which_list, int n);
 void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
 void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);

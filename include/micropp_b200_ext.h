@@ -52,6 +52,8 @@ int micropp3x_nndim(const struct micropp3 *self);
 int micropp3x_wave_size(const struct micropp3 *self);
 /* distinct ELL row blocks of the implicit operator of an all-elastic RVE; 0 = one assembled matrix per slot */
 int micropp3x_implicit_rows(const struct micropp3 *self);
+/* -1: assembled matrices; else the implicit SpMV kernel in use: 0 simple, 1 tiled (cp.async), 2 tiled (TMA) */
+int micropp3x_implicit_kernel(const struct micropp3 *self);
 void micropp3x_get_elem_type(const struct micropp3 *self, int *out);
 void micropp3x_get_bmat(const struct micropp3 *self, double *out /* [8][6][24] */);
 void micropp3x_get_ctan_lin(const struct micropp3 *self, double *out36);
@@ -65,6 +67,10 @@ void micropp3x_assembly_mat(struct micropp3 *self, const double *u, const double
 void micropp3x_newton(struct micropp3 *self, const double *eps, const double *vars_old, double *u, int *out3);
 void micropp3x_ave_stress(struct micropp3 *self, const double *u, const double *vars_old, double *sig);
 int micropp3x_vars_new(struct micropp3 *self, const double *u, const double *vars_old, double *vars_new);
+/* Ap = A p with the Jacobian at u = 0 without history (ell_mvp of src/ell.cpp:35-44 on the matrix assembly_mat
+   builds), through the chosen DPCG operator: op 0 = assembled ELL matrix, 3 = implicit operator of an all-elastic
+   RVE (kernel 0 simple / 1 tiled / -1 default).  p, Ap in the reference's layout [node][3]; returns p.Ap */
+double micropp3x_apply_operator(struct micropp3 *self, const double *p, double *Ap, int op, int kernel);
 
 /* ELL pieces */
 void micropp3x_ell_cols(int nx, int ny, int nz, int *cols);

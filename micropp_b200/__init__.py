@@ -98,6 +98,8 @@ def load():
         "micropp3x_nelem": (C.c_int, [H]),
         "micropp3x_nndim": (C.c_int, [H]),
         "micropp3x_wave_size": (C.c_int, [H]), "micropp3x_implicit_rows": (C.c_int, [H]),
+        "micropp3x_implicit_kernel": (C.c_int, [H]),
+        "micropp3x_apply_operator": (C.c_double, [H, _dp, _dp, C.c_int, C.c_int]),
         "micropp3x_get_elem_type": (None, [H, _ip]),
         "micropp3x_get_bmat": (None, [H, _dp]),
         "micropp3x_get_ctan_lin": (None, [H, _dp]),
@@ -269,6 +271,17 @@ class Micropp3:
     # ---- inspection -----------------------------------------------------------------------------
     def wave_size(self):
         return int(self.lib.micropp3x_wave_size(C.byref(self.h)))
+
+    def apply_operator(self, p, op=0, kernel=-1):
+        """(A p, p.Ap) with the Jacobian at u = 0 through DPCG operator `op` (0 assembled ELL, 3 implicit)."""
+        p = _f64(p)
+        out = np.zeros(self.nndim)
+        pap = self.lib.micropp3x_apply_operator(C.byref(self.h), _d(p), _d(out), int(op), int(kernel))
+        return out, float(pap)
+
+    def implicit_kernel(self):
+        """-1: assembled ELL matrices; else the implicit SpMV kernel: 0 simple, 1 tiled (cp.async), 2 tiled (TMA)."""
+        return int(self.lib.micropp3x_implicit_kernel(C.byref(self.h)))
 
     def implicit_rows(self):
         return int(self.lib.micropp3x_implicit_rows(C.byref(self.h)))

@@ -14,6 +14,7 @@
 // Assembly is a *gather by node* instead of the reference's element scatter: each ELL value is
 // written exactly once, coalesced, with the element contributions added in the reference's element
 // visiting order -- no atomics, no colours, no read-modify-write traffic.
+#include <cuda.h>  // CUtensorMap (type + enums only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -40,6 +41,9 @@ namespace {
 
 constexpr int NT = 128;      // threads per block of node/element kernels
 constexpr int NPLANE = 243;  // 27 neighbours x 3 x 3
+// row blocks of the implicit operator: [27 neighbours][10] doubles, the 3x3 block of a neighbour in the first 9 --
+// 80-B groups are 16-B aligned, so a neighbour's block is five 128-bit loads (global or shared)
+constexpr int RB_NBR = 10, RB_LEN = 27 * RB_NBR;
 constexpr int NLIST = 6;
 constexpr int NRED = 6;      // max values reduced per kernel
 
@@ -514,9 +518,15 @@ __global__ void __launch_bounds__(NT)
     et[c] = code % 3;
     code /= 3;
   }
-  AsmElasticLoop<0>::run(s_ke, et, rows + (size_t)id * NPLANE, 1);
+  double blk[NPLANE];
+  AsmElasticLoop<0>::run(s_ke, et, blk, 1);
+  double *out = rows + (size_t)id * RB_LEN;
+  for (int nbr = 0; nbr < 27; ++nbr) {
+    for (int q = 0; q < 9; ++q) out[nbr * RB_NBR + q] = blk[nbr * 9 + q];
+    out[nbr * RB_NBR + 9] = 0.0;
+  }
 #pragma unroll
-  for (int d = 0; d < 3; ++d) rkinv[id * 3 + d] = 1 / rows[(size_t)id * NPLANE + 13 * 9 + d * 4];
+  for (int d = 0; d < 3; ++d) rkinv[id * 3 + d] = 1 / blk[13 * 9 + d * 4];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -829,31 +839,32 @@ __global__ void __launch_bounds__(NT, 3)
     double y[R][3];
 #pragma unroll
     for (int r = 0; r < R; ++r) y[r][0] = y[r][1] = y[r][2] = 0.0;
-    const double *a = V.rows + (size_t)__ldg(&V.rowid[m]) * NPLANE;
+    const double *a = V.rows + (size_t)__ldg(&V.rowid[m]) * RB_LEN;
     // rolled over the 9 (dz, dy) neighbour rows, unrolled over dx: bounds the loads the scheduler can hoist
 #pragma unroll 1
     for (int row = 0; row < 9; ++row) {
       const int dk = row / 3 - 1, dj = row - (dk + 1) * 3 - 1;
       const int q0 = n + dj * P.nx + dk * P.nxny;
-      const double *ar = a + row * 27;
+      const double *ar = a + row * 3 * RB_NBR;
 #pragma unroll
       for (int di = -1; di <= 1; ++di) {
-        double av[9];
+        double av[10];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) av[t] = __ldg(ar + (di + 1) * 9 + t);
+        for (int t = 0; t < 5; ++t) {
+          const double2 v = __ldg(reinterpret_cast<const double2 *>(ar + (di + 1) * RB_NBR) + t);
+          av[2 * t] = v.x;
+          av[2 * t + 1] = v.y;
+        }
+        // component-outer order: 3R independent DFMAs between two updates of the same accumulator
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const double *pp = V.p + ((size_t)off[r] + (q0 + di));
-          const double px = pp[0], py = pp[npad], pz = pp[2 * npad];
-          y[r][0] += av[0] * px;
-          y[r][0] += av[1] * py;
-          y[r][0] += av[2] * pz;
-          y[r][1] += av[3] * px;
-          y[r][1] += av[4] * py;
-          y[r][1] += av[5] * pz;
-          y[r][2] += av[6] * px;
-          y[r][2] += av[7] * py;
-          y[r][2] += av[8] * pz;
+        for (int fj = 0; fj < 3; ++fj) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const double pval = V.p[(size_t)off[r] + (size_t)fj * npad + (q0 + di)];
+            y[r][0] += av[fj] * pval;
+            y[r][1] += av[3 + fj] * pval;
+            y[r][2] += av[6 + fj] * pval;
+          }
         }
       }
     }
@@ -903,6 +914,416 @@ __global__ void __launch_bounds__(NT, 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled version of the implicit SpMV (the default): k_spmv_dot_imp is bound by L1 wavefronts (81 p loads per
+// node, ncu: l1tex 72 %, FP64 pipe 25 %), so this kernel stages p through shared memory and blocks 8 x-adjacent
+// nodes per thread: a thread needs 10 x 9 x 3 p values for its 8 nodes (34 per node instead of 81), fetched as
+// conflict-free 128-bit shared loads, which leaves the FP64 pipe (243 DFMA per node) as the bound.
+//   block  = cb warps; warp w owns x-chunk w of the tile (8 nodes), lane l owns the (y, z) row (l & 7, l >> 3):
+//            a tile is 8cb x 8 x 4 interior nodes, its p brick (8cb+2) x 10 x 6 x 3 doubles;
+//   smem   : brick[d][bz][by][pitch = 8cb+2]; lanes of a quarter-warp differ in by => their 16-B accesses are
+//            pitch*8 B apart, and (8cb+2)/2 is odd, so they cover all 32 banks;
+//   rows   : almost every thread's 8 nodes share ONE row block (chunk_id >= 0): 243 L1-broadcast loads per 8 nodes;
+//            chunks that straddle a material interface (chunk_id < 0) fetch the row block of each node.
+// The FMA order per node is that of k_spmv_dot, so Ap is bit-identical; p.Ap is summed in a different (fixed) order.
+// ------------------------------------------------------------------------------------------------
+struct TileInfo {
+  int cb, tiles_x, tiles_y, tiles_z, nchunk, pitch;
+  const int *chunk_id;  // [niz][niy][nchunk]: row-block id shared by the chunk's nodes, or -1
+};
+constexpr int TILE_Y = 8, TILE_Z = 4, BRICK_ROWS = (TILE_Y + 2) * (TILE_Z + 2);
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// UNIFORM: every node of the thread uses the row block `a_uni` (shared-memory copy of a pure-material block);
+// otherwise node t uses rows[rid[t]] (global, L1).
+template <bool UNIFORM>
+__device__ __forceinline__ void tile_rows_apply(const double *__restrict__ a_uni, const double *__restrict__ rows,
+                                                const int (&rid)[8], const double *__restrict__ brick, int pitch,
+                                                int bx0, int ry, int rz, double (&acc)[8][3]) {
+#pragma unroll(UNIFORM ? 3 : 1)
+  for (int row = 0; row < 9; ++row) {
+    const int dk = row / 3, dj = row - dk * 3;  // 0..2 (offset + 1)
+    const int rbase = ((rz + dk) * (TILE_Y + 2) + (ry + dj)) * pitch + bx0;
+    double pv[3][10];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double2 *s2 = reinterpret_cast<const double2 *>(brick + d * (BRICK_ROWS * pitch) + rbase);
+#pragma unroll
+      for (int h = 0; h < 5; ++h) {
+        const double2 v = s2[h];
+        pv[d][2 * h] = v.x;
+        pv[d][2 * h + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const int ao = (row * 3 + di) * RB_NBR;
+      if (UNIFORM) {
+        double av[10];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const double2 v = reinterpret_cast<const double2 *>(a_uni + ao)[q];
+          av[2 * q] = v.x;
+          av[2 * q + 1] = v.y;
+        }
+        // component-outer order: 24 independent DFMAs between two updates of the same accumulator (each accumulator
+        // still receives its px, py, pz terms in this order)
+#pragma unroll
+        for (int fj = 0; fj < 3; ++fj) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const double pval = pv[fj][t + di];
+            acc[t][0] += av[fj] * pval;
+            acc[t][1] += av[3 + fj] * pval;
+            acc[t][2] += av[6 + fj] * pval;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const double2 *a2 = reinterpret_cast<const double2 *>(rows + (size_t)rid[t] * RB_LEN + ao);
+          double av[10];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const double2 v = __ldg(a2 + q);
+            av[2 * q] = v.x;
+            av[2 * q + 1] = v.y;
+          }
+          const double px = pv[0][t + di], py = pv[1][t + di], pz = pv[2][t + di];
+          acc[t][0] += av[0] * px;
+          acc[t][0] += av[1] * py;
+          acc[t][0] += av[2] * pz;
+          acc[t][1] += av[3] * px;
+          acc[t][1] += av[4] * py;
+          acc[t][1] += av[5] * pz;
+          acc[t][2] += av[6] * px;
+          acc[t][2] += av[7] * py;
+          acc[t][2] += av[8] * pz;
+        }
+      }
+    }
+  }
+}
+
+// about 384 threads x 168 registers per SM: 3 blocks of 4 warps, 2 of 6, ...
+template <int CB>
+__global__ void __launch_bounds__(32 * CB, (384 / (32 * CB)) > 0 ? 384 / (32 * CB) : 1)
+    k_spmv_dot_tile(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, TileInfo ti,
+                    int force) {
+  extern __shared__ __align__(16) double s_brick[];  // [3][BRICK_ROWS][pitch]
+  __shared__ __align__(16) double s_rows[3 * RB_LEN];  // row blocks 0..2 = nodes surrounded by one material
+  __shared__ double s_red[8];
+  __shared__ int sflag;
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!force && !st->cg_active) return;
+  for (int q = threadIdx.x; q < 3 * RB_LEN; q += 32 * CB) s_rows[q] = __ldg(&V.rows[q]);
+  const size_t vo = (size_t)slot * V.vstride;
+  const double *p = V.p + vo;
+  double *Ap = V.Ap + vo;
+  const size_t npad = P.nn_pad;
+  constexpr int pitch = 8 * CB + 2, nw = CB;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x;
+  const int tx = b % ti.tiles_x;
+  b /= ti.tiles_x;
+  const int ty = b % ti.tiles_y, tz = b / ti.tiles_y;
+  const int X0 = tx * 8 * CB, Y0 = ty * TILE_Y, Z0 = tz * TILE_Z;  // grid coordinates of the brick origin
+
+  // ---- p brick -> shared memory (rows of the brick are contiguous in global memory) ----
+  for (int r = w; r < 3 * BRICK_ROWS; r += nw) {
+    const int d = r / BRICK_ROWS, rr = r - d * BRICK_ROWS, bz = rr / (TILE_Y + 2), by = rr - bz * (TILE_Y + 2);
+    const int gy = Y0 + by, gz = Z0 + bz;
+    const bool row_in = gy < P.ny && gz < P.nz;
+    const double *src = p + (size_t)d * npad + (size_t)gz * P.nxny + gy * P.nx + X0;
+    double *dst = s_brick + r * pitch;
+    for (int bx = lane; bx < pitch; bx += 32) {
+      if (row_in && X0 + bx < P.nx)
+        cp_async8(dst + bx, src + bx);
+      else
+        dst[bx] = 0.0;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- 8 nodes per thread ----
+  const int ry = lane & 7, rz = lane >> 3;
+  const int c = tx * CB + w, jj = Y0 + ry, kk = Z0 + rz;  // chunk, interior y, interior z (0-based)
+  double red = 0.0;
+  const bool work = c < ti.nchunk && jj < P.niy && kk < P.niz;
+  int cid = 0;
+  if (work) cid = __ldg(&ti.chunk_id[(kk * P.niy + jj) * ti.nchunk + c]);
+  // one path per warp: the per-node row path only when some lane's chunk straddles a material interface
+  const bool uniform = __all_sync(0xffffffffu, !work || (cid >= 0 && cid < 3));
+  if (work) {
+    const int ii0 = c * 8;
+    const int nvalid = min(8, P.nix - ii0);
+    const int m0 = (kk * P.niy + jj) * P.nix + ii0;
+    double acc[8][3];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+    int rid[8];
+    if (uniform) {
+      rid[0] = cid;
+      tile_rows_apply<true>(s_rows + cid * RB_LEN, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) rid[t] = cid >= 0 ? cid : __ldg(&V.rowid[m0 + min(t, nvalid - 1)]);
+      tile_rows_apply<false>(s_rows, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
+    }
+    const int n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
+    const int cbase = ((rz + 1) * (TILE_Y + 2) + (ry + 1)) * pitch + 8 * w + 1;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < nvalid) {
+        Ap[n0 + t] = acc[t][0];
+        Ap[npad + n0 + t] = acc[t][1];
+        Ap[2 * npad + n0 + t] = acc[t][2];
+        red += s_brick[cbase + t] * acc[t][0] + s_brick[BRICK_ROWS * pitch + cbase + t] * acc[t][1] +
+               s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
+      }
+    }
+  }
+
+  // ---- p.Ap: deterministic ticket reduction over the tiles of this slot ----
+  red = warp_sum(red);
+  if (lane == 0) s_red[w] = red;
+  __syncthreads();
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int ww = 0; ww < nw; ++ww) s += s_red[ww];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    sflag = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!sflag) return;
+  __threadfence();
+  double acc2 = 0.0;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += 32 * CB) acc2 += __ldcg(&partial[q]);
+  acc2 = warp_sum(acc2);
+  __syncthreads();
+  if (lane == 0) s_red[w] = acc2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int ww = 0; ww < nw; ++ww) s += s_red[ww];
+    st->ticket = 0u;
+    if (P.slab)
+      T.red[slot * 8] = s;
+    else
+      tail_spmv(st, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA version of the tiled implicit SpMV (default whenever nx is even: TMA needs 16-B global strides).  The p brick of
+// a (tile, slot) item -- (8cb+2) x 10 x 6 nodes x 3 components -- is ONE cp.async.bulk.tensor.5d from the pool
+// viewed as a rank-5 tensor (x, y, z, component, slot); out-of-grid parts are zero-filled by the TMA unit.  A block
+// walks over its items (ntl consecutive tiles x rs slots) with a two-stage mbarrier pipeline: thread 0 arms the
+// barrier and issues the load of item i+1 before the block computes item i, so the brick traffic (L2 -> smem)
+// overlaps the FP64 work and costs no issue slots of the compute warps.  Compute, row tables and the per-slot
+// deterministic reduction are those of k_spmv_dot_tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int FOLD_PLANE = 2;  // planes 0/1 of the partial-sum buffer belong to the consumer's own grid_sum<2>
+
+// sum of the n per-(tile, warp) partials of a slot, by ONE warp, in a fixed order; result in every lane
+__device__ __forceinline__ double fold_partials(const double *partial, int n) {
+  double acc = 0.0;
+  for (int q = threadIdx.x & 31; q < n; q += 32) acc += __ldcg(&partial[q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+// slab mode / forced applications: fold p.Ap right after the SpMV (one warp per slot)
+__global__ void k_fold_spmv(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, int nfold, int force) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!force && !st->cg_active) return;
+  const double s = fold_partials(T.partial + ((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max, nfold);
+  if (threadIdx.x == 0) {
+    if (P.slab)
+      T.red[slot * 8] = s;
+    else
+      tail_spmv(st, s);
+  }
+}
+
+constexpr int TMA_MAX_RS = 8;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+      "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+template <int CB>
+__global__ void __launch_bounds__(32 * CB, CB <= 4 ? 2 : 1)
+    k_spmv_dot_tma(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V, TileInfo ti,
+                   const __grid_constant__ CUtensorMap tmap, int ntl, int rs, int force) {
+  extern __shared__ unsigned char s_raw[];
+  constexpr int pitch = 8 * CB + 2;
+  constexpr int BRICK = 3 * BRICK_ROWS * pitch;                       // doubles
+  constexpr int STAGE_BYTES = (BRICK * 8 + 127) / 128 * 128;
+  __shared__ uint64_t s_full[2];
+  __shared__ int s_slot[TMA_MAX_RS];
+  __shared__ __align__(16) double s_rows[3 * RB_LEN];  // row blocks 0..2 = nodes surrounded by one material
+  __shared__ int s_done[2];
+  // 128-B aligned stages; plain array arithmetic keeps the pointer in the shared address space (LDS, not generic LD)
+  unsigned char *s_base = s_raw + ((128u - ((unsigned)__cvta_generic_to_shared(s_raw) & 127u)) & 127u);
+  for (int q = threadIdx.x; q < 3 * RB_LEN; q += 32 * CB) s_rows[q] = __ldg(&V.rows[q]);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+  const int tile0 = blockIdx.x * ntl;
+  const int nitems = min(ntl, ntiles - tile0) * rs;
+
+  if ((int)threadIdx.x < rs) {
+    const int yy = (int)blockIdx.y * rs + (int)threadIdx.x + L.yoff;
+    const int cnt = L.dcount ? min(*L.dcount, n_list + L.yoff) : n_list + L.yoff;
+    int slot = yy < cnt ? L.list[yy] : -1;
+    if (slot >= 0 && !force && !T.state[slot].cg_active) slot = -1;
+    s_slot[threadIdx.x] = slot;
+  }
+  if (threadIdx.x == 0) {
+    s_done[0] = s_done[1] = 0;
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto next_active = [&](int i) {
+    while (i < nitems && s_slot[i % rs] < 0) ++i;
+    return i;
+  };
+  auto issue = [&](int item, int stage) {  // thread 0
+    const int tile = tile0 + item / rs, slot = s_slot[item % rs];
+    const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+    mbar_expect_tx(&s_full[stage], BRICK * 8);
+    tma_load_5d(s_base + stage * STAGE_BYTES, &tmap, &s_full[stage], tx * 8 * CB, ty * TILE_Y, tz * TILE_Z, 0, slot);
+  };
+
+  const int ry = lane & 7, rz = lane >> 3;
+  const size_t npad = P.nn_pad;
+  // Warps run through the items without block-wide barriers: a warp waits for the brick of its item (full barrier),
+  // computes, deposits its partial p.Ap, and signs the stage off; the LAST warp to sign off re-arms the stage with
+  // the load of the item after next.  Items 0 and 1 are issued up front.
+  int cur = next_active(0), k = 0;
+  if (threadIdx.x == 0 && cur < nitems) {
+    issue(cur, 0);
+    const int second = next_active(cur + 1);
+    if (second < nitems) issue(second, 1);
+  }
+  while (cur < nitems) {
+    const int nxt = next_active(cur + 1);
+    const int stage = k & 1;
+    const int tile = tile0 + cur / rs, slot = s_slot[cur % rs];
+    const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+    const double *s_brick = reinterpret_cast<const double *>(s_base + stage * STAGE_BYTES);
+    mbar_wait(&s_full[stage], (k >> 1) & 1);
+
+    const int c = tx * CB + w, jj = ty * TILE_Y + ry, kk = tz * TILE_Z + rz;
+    double red = 0.0;
+    const bool work = c < ti.nchunk && jj < P.niy && kk < P.niz;
+    int cid = 0;
+    if (work) cid = __ldg(&ti.chunk_id[(kk * P.niy + jj) * ti.nchunk + c]);
+    // one path per warp: the per-node row path only when some lane's chunk straddles a material interface
+    const bool uniform = __all_sync(0xffffffffu, !work || (cid >= 0 && cid < 3));
+    if (work) {
+      const int ii0 = c * 8;
+      const int nvalid = min(8, P.nix - ii0);
+      const int m0 = (kk * P.niy + jj) * P.nix + ii0;
+      double acc[8][3];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+      int rid[8];
+      if (uniform) {
+        rid[0] = cid;
+        tile_rows_apply<true>(s_rows + cid * RB_LEN, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rid[t] = cid >= 0 ? cid : __ldg(&V.rowid[m0 + min(t, nvalid - 1)]);
+        tile_rows_apply<false>(s_rows, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
+      }
+      double *Ap = V.Ap + (size_t)slot * V.vstride;
+      const int n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
+      const int cbase = ((rz + 1) * (TILE_Y + 2) + (ry + 1)) * pitch + 8 * w + 1;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < nvalid) {
+          Ap[n0 + t] = acc[t][0];
+          Ap[npad + n0 + t] = acc[t][1];
+          Ap[2 * npad + n0 + t] = acc[t][2];
+          red += s_brick[cbase + t] * acc[t][0] + s_brick[BRICK_ROWS * pitch + cbase + t] * acc[t][1] +
+                 s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
+        }
+      }
+    }
+    __syncwarp();
+
+    // stage sign-off; the last warp re-arms the stage with the item after next
+    if (lane == 0) {
+      const int done = atomicAdd(&s_done[stage], 1);
+      if (done == CB - 1) {
+        s_done[stage] = 0;
+        const int after = nxt < nitems ? next_active(nxt + 1) : nitems;
+        if (after < nitems) {
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          issue(after, stage);
+        }
+      }
+    }
+
+    // p.Ap of this slot: one partial per (tile, warp) in plane FOLD_PLANE of the slot's partial-sum buffer.  No
+    // ticket, no fence: the sum is folded in a fixed order by k_fold_spmv (one warp per slot), which the kernel
+    // boundary orders after these stores.
+    red = warp_sum(red);
+    if (lane == 0) T.partial[((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max + tile * CB + w] = red;
+    cur = nxt;
+    ++k;
+  }
+}
+
 __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, int n, int d) {
   int i, j, k;
   node_ijk(P, n, i, j, k);
@@ -914,24 +1335,52 @@ __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, i
 // cg_update / cg_pupdate of the implicit operator: k = 1/diag comes from the row table and z = k r is recomputed
 // instead of being stored (the same multiplication => the same bits); 144 + 72 B/node instead of 192 + 72.
 __global__ void __launch_bounds__(NT)
-    k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+    k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int nfold) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
+  __shared__ double s_alpha;
   const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
-  const double alpha = st->alpha;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
+  // the vector loads go out first: the fold below (and its barrier) then overlaps their latency
+  double pp[3], rr[3], ap[3], dd[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const size_t ix = vo + (size_t)d * P.nn_pad + (n < P.nn ? n : 0);
+    pp[d] = V.p[ix];
+    rr[d] = V.r[ix];
+    ap[d] = V.Ap[ix];
+    dd[d] = V.du[ix];
+  }
+  double alpha;
+  if (nfold > 0) {
+    // the TMA SpMV left per-(tile, warp) partials of p.Ap: every block folds them itself (same order => same bits)
+    if (threadIdx.x < 32) {
+      const double pAp = fold_partials(T.partial + ((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max, nfold);
+      if (threadIdx.x == 0) {
+        const double a = st->rz / pAp;  // src/ell.cpp:100
+        s_alpha = a;
+        if (blockIdx.x == 0) {
+          st->pAp = pAp;
+          st->alpha = a;
+        }
+      }
+    }
+    __syncthreads();
+    alpha = s_alpha;
+  } else {
+    alpha = st->alpha;
+  }
   double red[2] = {0.0, 0.0};
   if (n < P.nn) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double pp = V.p[ix];
-      V.du[ix] += alpha * pp;
-      const double r = V.r[ix] - alpha * V.Ap[ix];
+      V.du[ix] = dd[d] + alpha * pp[d];
+      const double r = rr[d] - alpha * ap[d];
       V.r[ix] = r;
       const double z = __dmul_rn(imp_kk(P, V, n, d), r);  // rounded product, as when z is stored (k_cg_update)
       red[0] += z * z;
@@ -1279,6 +1728,12 @@ struct mgpu_ctx {
   int mat_slots = 0;      // slots of the explicit matrix pool
   int cg_op = OP_SLOT;    // operator of the DPCG solve in flight (set by mgpu_cg_init)
   int nrows = 0;
+  TileInfo tile{};        // tiled implicit SpMV (k_spmv_dot_tile)
+  int *d_chunk_id = nullptr;
+  int tile_smem = 0;
+  int imp_kernel = 1;     // 2 tiled + TMA (default when nx is even), 1 tiled + cp.async, 0 simple (MICROPP_IMP_KERNEL)
+  CUtensorMap tmap_p;     // V.p as a rank-5 tensor (x, y, z, component, slot)
+  int tma_smem = 0;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
   double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
@@ -1328,6 +1783,35 @@ inline Lst lst_of(const mgpu_ctx *c, int l, int off = 0) { return Lst{c->d_list[
 inline dim3 int_grid(const mgpu_ctx *c, int n) { return dim3(std::max((c->mc.nint + NT - 1) / NT, 1), n, 1); }
 inline dim3 node_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT - 1) / NT, n, 1); }
 inline dim3 elem_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nelem + NT - 1) / NT, n, 1); }
+
+typedef void (*tile_kernel_t)(const MeshConst, const Lst, SlotTables, VecPool, TileInfo, int);
+inline tile_kernel_t tile_kernel(int cb) {
+  switch (cb) {
+    case 1: return k_spmv_dot_tile<1>;
+    case 2: return k_spmv_dot_tile<2>;
+    case 3: return k_spmv_dot_tile<3>;
+    case 4: return k_spmv_dot_tile<4>;
+    case 5: return k_spmv_dot_tile<5>;
+    case 6: return k_spmv_dot_tile<6>;
+    case 7: return k_spmv_dot_tile<7>;
+    default: return k_spmv_dot_tile<8>;
+  }
+}
+
+typedef void (*tma_kernel_t)(const MeshConst, const Lst, int, SlotTables, VecPool, TileInfo, const CUtensorMap, int, int,
+                             int);
+inline tma_kernel_t tma_kernel(int cb) {
+  switch (cb) {
+    case 1: return k_spmv_dot_tma<1>;
+    case 2: return k_spmv_dot_tma<2>;
+    case 3: return k_spmv_dot_tma<3>;
+    case 4: return k_spmv_dot_tma<4>;
+    case 5: return k_spmv_dot_tma<5>;
+    case 6: return k_spmv_dot_tma<6>;
+    case 7: return k_spmv_dot_tma<7>;
+    default: return k_spmv_dot_tma<8>;
+  }
+}
 
 struct ProfScope {
   mgpu_ctx *c;
@@ -1620,6 +2104,10 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   if (c->implicit) {
     // distinct row blocks: code = sum_c type_c 3^c over the 8 elements around an interior node
     std::vector<int> code2id(6561, -1), codes, rowid(P.nint_pad, 0);
+    for (int t = 0; t < 3; ++t) {  // ids 0..2: nodes whose 8 elements are all of material t (kept in shared memory)
+      code2id[t * 3280] = t;
+      codes.push_back(t * 3280);
+    }
     for (int m = 0; m < P.nint; ++m) {
       const int pl = P.nix * P.niy;
       const int kk = m / pl, r = m - kk * pl, jj = r / P.nix, ii = r - jj * P.nix;
@@ -1641,7 +2129,7 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     double *d_rows = nullptr, *d_rkinv = nullptr;
     CK(cudaMalloc(&d_codes, sizeof(int) * c->nrows));
     CK(cudaMalloc(&d_rowid, sizeof(int) * P.nint_pad));
-    CK(cudaMalloc(&d_rows, sizeof(double) * NPLANE * c->nrows));
+    CK(cudaMalloc(&d_rows, sizeof(double) * RB_LEN * c->nrows));
     CK(cudaMalloc(&d_rkinv, sizeof(double) * 3 * c->nrows));
     CK(cudaMemcpy(d_codes, codes.data(), sizeof(int) * c->nrows, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_rowid, rowid.data(), sizeof(int) * P.nint_pad, cudaMemcpyHostToDevice));
@@ -1653,6 +2141,70 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     V.rows = d_rows;
     V.rkinv = d_rkinv;
     V.rowid = d_rowid;
+
+    // tiling of k_spmv_dot_tile: chunks of 8 x-adjacent interior nodes, cb chunks (warps) per block
+    TileInfo &ti = c->tile;
+    ti.nchunk = (P.nix + 7) / 8;
+    // blocks of 4 warps (2 resident blocks of 2 x 49 KB stages per SM) unless that idles too many warps
+    int best_cb = 1;
+    double best_score = 1e30;
+    for (int cb = 1; cb <= std::min(ti.nchunk, 4); ++cb) {
+      const int warps = (ti.nchunk + cb - 1) / cb * cb;  // executed warps per row block, idle ones included
+      const double score = warps * (cb == 4 ? 1.0 : cb == 3 ? 1.15 : 1.5);
+      if (score < best_score) {
+        best_score = score;
+        best_cb = cb;
+      }
+    }
+    ti.cb = best_cb;
+    ti.tiles_x = (ti.nchunk + ti.cb - 1) / ti.cb;
+    ti.tiles_y = (P.niy + TILE_Y - 1) / TILE_Y;
+    ti.tiles_z = (P.niz + TILE_Z - 1) / TILE_Z;
+    ti.pitch = 8 * ti.cb + 2;
+    c->tile_smem = (int)(sizeof(double) * 3 * BRICK_ROWS * ti.pitch);
+    std::vector<int> chunk_id((size_t)P.niz * P.niy * ti.nchunk, -1);
+    for (int kk = 0; kk < P.niz; ++kk)
+      for (int jj = 0; jj < P.niy; ++jj)
+        for (int cc = 0; cc < ti.nchunk; ++cc) {
+          const int m0 = (kk * P.niy + jj) * P.nix + cc * 8, nv = std::min(8, P.nix - cc * 8);
+          int id = rowid[m0];
+          for (int t = 1; t < nv; ++t)
+            if (rowid[m0 + t] != id) id = -1;
+          chunk_id[((size_t)kk * P.niy + jj) * ti.nchunk + cc] = id;
+        }
+    CK(cudaMalloc(&c->d_chunk_id, sizeof(int) * chunk_id.size()));
+    CK(cudaMemcpy(c->d_chunk_id, chunk_id.data(), sizeof(int) * chunk_id.size(), cudaMemcpyHostToDevice));
+    ti.chunk_id = c->d_chunk_id;
+    CK(cudaFuncSetAttribute(tile_kernel(ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize, c->tile_smem));
+    c->imp_kernel = 1;
+    if (P.nx % 2 == 0) {
+      // TMA descriptor of the p pool; the encoder comes from the driver through the runtime (no -lcuda)
+      typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+          qres == cudaDriverEntryPointSuccess) {
+        const cuuint64_t gdim[5] = {(cuuint64_t)P.nx, (cuuint64_t)P.ny, (cuuint64_t)P.nz, 3, (cuuint64_t)W};
+        const cuuint64_t gstr[4] = {(cuuint64_t)P.nx * 8, (cuuint64_t)P.nxny * 8, (cuuint64_t)P.nn_pad * 8,
+                                    (cuuint64_t)vlen * 8};
+        const cuuint32_t box[5] = {(cuuint32_t)ti.pitch, TILE_Y + 2, TILE_Z + 2, 3, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = ((encode_t)fn)(&c->tmap_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void *)V.p, gdim, gstr, box,
+                                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+          c->imp_kernel = 2;
+          c->tma_smem = 2 * ((c->tile_smem + 127) / 128 * 128) + 128;
+          CK(cudaFuncSetAttribute(tma_kernel(ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize, c->tma_smem));
+        } else {
+          fprintf(stderr, "micropp-b200: cuTensorMapEncodeTiled failed (%d); using the cp.async tiled kernel\n", (int)r);
+        }
+      }
+    }
+    if (const char *env = getenv("MICROPP_IMP_KERNEL")) c->imp_kernel = std::min(c->imp_kernel, std::max(atoi(env), 0));
+    if (ti.tiles_x * ti.tiles_y * ti.tiles_z > nblk_max) c->imp_kernel = 0;  // partial-sum buffer too small
   }
 
   SlotTables &T = c->T;
@@ -1705,6 +2257,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   if (c->V.rows) cudaFree((void *)c->V.rows);
   if (c->V.rkinv) cudaFree((void *)c->V.rkinv);
   if (c->V.rowid) cudaFree((void *)c->V.rowid);
+  if (c->d_chunk_id) cudaFree(c->d_chunk_id);
   cudaFree(c->T.state);
   cudaFree((void *)c->T.vars_old);
   cudaFree((void *)c->T.vars_new);
@@ -1920,6 +2473,41 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
 int mgpu_implicit(const mgpu_ctx *c) { return c->implicit ? 1 : 0; }
 int mgpu_implicit_rows(const mgpu_ctx *c) { return c->nrows; }
 
+// the implicit SpMV kernel a request resolves to: 0 simple, 1 tiled (cp.async), 2 tiled (TMA)
+static int imp_kernel_of(const mgpu_ctx *c, int kern) {
+  const TileInfo &ti = c->tile;
+  const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+  return std::min(kern, (c->imp_kernel == 2 && ntiles * ti.cb <= c->T.nblk_max) ? 2 : (ntiles <= c->T.nblk_max ? 1 : 0));
+}
+// partials of p.Ap that k_cg_update_imp would fold itself: measured slower (0.2 ms per DPCG iteration of 1024 RVEs at
+// 30^3: every block repeats the fold before its stores) than the one-warp-per-slot k_fold_spmv launch => disabled
+static int imp_fold_count(const mgpu_ctx *c) {
+  (void)c;
+  return 0;
+}
+// Ap = A p of the implicit operator over n entries of list l
+static void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
+  const TileInfo &ti = c->tile;
+  const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+  kern = imp_kernel_of(c, kern);
+  if (kern == 2) {
+    const int rs = std::min(TMA_MAX_RS, n), ntl = rs >= 4 ? 1 : TMA_MAX_RS / rs;
+    tma_kernel(ti.cb)<<<dim3((ntiles + ntl - 1) / ntl, (n + rs - 1) / rs), 32 * ti.cb, c->tma_smem, c->stream>>>(
+        c->mc, lst_of(c, l), n, c->T, c->V, ti, c->tmap_p, ntl, rs, force);
+    // p.Ap: one warp per slot folds the per-(tile, warp) partials in a fixed order and runs the scalar tail
+    k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, ntiles * ti.cb, force);
+    c->launches++;
+  } else if (kern == 1) {
+    tile_kernel(ti.cb)<<<dim3(ntiles, n), 32 * ti.cb, c->tile_smem, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, ti,
+                                                                                 force);
+  } else {
+    k_spmv_dot_imp<MR><<<int_grid(c, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, force);
+  }
+}
+
+// -1: no implicit operator; else the SpMV kernel it runs (0 simple, 1 tiled cp.async, 2 tiled TMA)
+int mgpu_implicit_kernel(const mgpu_ctx *c) { return c->implicit ? imp_kernel_of(c, c->imp_kernel) : -1; }
+
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   if (use_shared == OP_IMPLICIT && !c->implicit) {
@@ -1935,7 +2523,7 @@ void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
   if (use_shared == OP_IMPLICIT) {
-    k_spmv_dot_imp<MR><<<int_grid(c, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, 0);
+    launch_imp_spmv(c, l, n, 0, c->imp_kernel);
   } else {
     k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
   }
@@ -1945,7 +2533,7 @@ void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
   if (c->cg_op == OP_IMPLICIT)
-    k_cg_update_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+    k_cg_update_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, imp_fold_count(c));
   else
     k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
@@ -2248,6 +2836,27 @@ void mgpu_spmv_generic(mgpu_ctx *c, int l, int n, int force) {
   if (n <= 0) return;
   ProfScope ps(c, 0, n);
   k_spmv_generic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, force);
+  CK(cudaGetLastError());
+}
+
+// One forced operator application on the slots of a list (parity tests of the SpMV kernels): Ap = A p with p as
+// it stands in the pool; op as in mgpu_cg_init; imp_kernel: -1 the context's choice, 0 simple, 1 tiled
+void mgpu_apply_operator(mgpu_ctx *c, int l, int n, int op, int imp_kernel) {
+  if (n <= 0) return;
+  CK(cudaSetDevice(c->device));
+  c->launches++;
+  const int kern = imp_kernel < 0 ? c->imp_kernel : imp_kernel;
+  if (op == OP_IMPLICIT) {
+    if (!c->implicit) {
+      fprintf(stderr, "micropp-b200: implicit operator requested for an RVE that is not all-elastic\n");
+      abort();
+    }
+    launch_imp_spmv(c, l, n, 1, kern);
+  } else if (op == OP_GENERIC) {
+    k_spmv_generic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, 1);
+  } else {
+    k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, op, 1);
+  }
   CK(cudaGetLastError());
 }
 

@@ -881,6 +881,28 @@ double micropp3x_last_homogenize_ms(const micropp3 *s) { return mpp_access::last
 unsigned long long micropp3x_launch_count(const micropp3 *s) {
   return mgpu_launch_count(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
 }
+int micropp3x_implicit_kernel(const micropp3 *s) {
+  return mgpu_implicit_kernel(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
+}
+double micropp3x_apply_operator(micropp3 *s, const double *p, double *Ap, int op, int kernel) {
+  micropp<3> *m = (micropp<3> *)s->ptr;
+  mpp_engine *e = mpp_access::engine(m);
+  const int slot0 = 0, none = -1;
+  mgpu_bind_slots(e->ctx, 1, &slot0, &none, nullptr);
+  mgpu_set_list(e->ctx, mpp_engine::L_SUB, 1, &slot0);
+  if (op == 0) {
+    mgpu_zero_u(e->ctx, mpp_engine::L_SUB, 1);
+    mgpu_asm_mat(e->ctx, mpp_engine::L_SUB, 1, 0);
+  }
+  std::vector<double> zero((size_t)mpp_access::nndim(m), 0.0);
+  mgpu_stage_put_vec(e->ctx, slot0, 2, zero.data());  // Ap of boundary rows is never written
+  mgpu_stage_put_vec(e->ctx, slot0, 3, p);
+  mgpu_apply_operator(e->ctx, mpp_engine::L_SUB, 1, op, kernel);
+  mgpu_stage_get_vec(e->ctx, slot0, 2, Ap);
+  mgpu_slot_state st;
+  mgpu_fetch_state(e->ctx, 1, &slot0, &st);
+  return st.pAp;
+}
 double micropp3x_bench_spmv(micropp3 *s, int nslots, int iters) {
   return mgpu_bench_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters);
 }
