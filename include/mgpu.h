@@ -112,6 +112,7 @@ void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_share
    of the last mgpu_cg_init */
 int mgpu_implicit(const mgpu_ctx *);
 int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
+int mgpu_implicit_fix_nodes(const mgpu_ctx *); /* interior nodes on material interfaces (fix-up list of the TMA kernel) */
 int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 simple, 1 tiled (cp.async), 2 tiled (TMA) */
 void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);

@@ -930,6 +930,11 @@ __global__ void __launch_bounds__(NT, 3)
 struct TileInfo {
   int cb, tiles_x, tiles_y, tiles_z, nchunk, pitch;
   const int *chunk_id;  // [niz][niy][nchunk]: row-block id shared by the chunk's nodes, or -1
+  // TMA kernel: every chunk is computed with ONE pure-material row block (id 0..2, shared memory) and the nodes of
+  // the chunk whose own block differs (material interfaces) are recomputed from the per-tile fix-up list
+  const int *chunk_pure;  // [niz][niy][nchunk]: pure id | (8-bit mask of the nodes to fix up) << 8
+  const int *fix_ptr;     // [ntiles + 1]
+  const int2 *fix;        // x: lx | ry << 8 | rz << 12 (position inside the tile), y: row-block id
 };
 constexpr int TILE_Y = 8, TILE_Z = 4, BRICK_ROWS = (TILE_Y + 2) * (TILE_Z + 2);
 
@@ -1010,6 +1015,14 @@ __device__ __forceinline__ void tile_rows_apply(const double *__restrict__ a_uni
       }
     }
   }
+}
+
+// every node of the thread uses the row block `a_uni` (shared memory)
+__device__ __forceinline__ void tile_rows_apply_uniform(const double *__restrict__ a_uni,
+                                                        const double *__restrict__ brick, int pitch, int bx0, int ry,
+                                                        int rz, double (&acc)[8][3]) {
+  const int rid[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  tile_rows_apply<true>(a_uni, nullptr, rid, brick, pitch, bx0, ry, rz, acc);
 }
 
 // about 384 threads x 168 registers per SM: 3 blocks of 4 warps, 2 of 6, ...
@@ -1254,43 +1267,42 @@ __global__ void __launch_bounds__(32 * CB, CB <= 4 ? 2 : 1)
     const int second = next_active(cur + 1);
     if (second < nitems) issue(second, 1);
   }
+  // per-tile thread state (independent of the slot: with ntl == 1 it is computed once per block)
+  int cur_tile = -1, pure = 0, keep = 0, n0 = 0, f0 = 0, f1 = 0, nfix0 = 0;
+  bool work = false;
   while (cur < nitems) {
     const int nxt = next_active(cur + 1);
     const int stage = k & 1;
     const int tile = tile0 + cur / rs, slot = s_slot[cur % rs];
-    const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+    if (tile != cur_tile) {
+      cur_tile = tile;
+      const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+      const int c = tx * CB + w, jj = ty * TILE_Y + ry, kk = tz * TILE_Z + rz;
+      work = c < ti.nchunk && jj < P.niy && kk < P.niz;
+      const int info = work ? __ldg(&ti.chunk_pure[(kk * P.niy + jj) * ti.nchunk + c]) : 0;
+      pure = info & 0xff;
+      const int ii0 = c * 8;
+      const int nvalid = min(8, P.nix - ii0);
+      keep = work ? (((1 << nvalid) - 1) & ~(info >> 8)) : 0;  // nodes this thread stores itself
+      n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
+      f0 = __ldg(&ti.fix_ptr[tile]);
+      f1 = __ldg(&ti.fix_ptr[tile + 1]);
+      nfix0 = (ty * TILE_Y + 1) * P.nx + (tz * TILE_Z + 1) * P.nxny + tx * 8 * CB + 1;  // node of tile position 0
+    }
     const double *s_brick = reinterpret_cast<const double *>(s_base + stage * STAGE_BYTES);
     mbar_wait(&s_full[stage], (k >> 1) & 1);
 
-    const int c = tx * CB + w, jj = ty * TILE_Y + ry, kk = tz * TILE_Z + rz;
     double red = 0.0;
-    const bool work = c < ti.nchunk && jj < P.niy && kk < P.niz;
-    int cid = 0;
-    if (work) cid = __ldg(&ti.chunk_id[(kk * P.niy + jj) * ti.nchunk + c]);
-    // one path per warp: the per-node row path only when some lane's chunk straddles a material interface
-    const bool uniform = __all_sync(0xffffffffu, !work || (cid >= 0 && cid < 3));
+    double *Ap = V.Ap + (size_t)slot * V.vstride;
     if (work) {
-      const int ii0 = c * 8;
-      const int nvalid = min(8, P.nix - ii0);
-      const int m0 = (kk * P.niy + jj) * P.nix + ii0;
       double acc[8][3];
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
-      int rid[8];
-      if (uniform) {
-        rid[0] = cid;
-        tile_rows_apply<true>(s_rows + cid * RB_LEN, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
-      } else {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) rid[t] = cid >= 0 ? cid : __ldg(&V.rowid[m0 + min(t, nvalid - 1)]);
-        tile_rows_apply<false>(s_rows, V.rows, rid, s_brick, pitch, 8 * w, ry, rz, acc);
-      }
-      double *Ap = V.Ap + (size_t)slot * V.vstride;
-      const int n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
+      tile_rows_apply_uniform(s_rows + pure * RB_LEN, s_brick, pitch, 8 * w, ry, rz, acc);
       const int cbase = ((rz + 1) * (TILE_Y + 2) + (ry + 1)) * pitch + 8 * w + 1;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        if (t < nvalid) {
+        if ((keep >> t) & 1) {
           Ap[n0 + t] = acc[t][0];
           Ap[npad + n0 + t] = acc[t][1];
           Ap[2 * npad + n0 + t] = acc[t][2];
@@ -1298,6 +1310,46 @@ __global__ void __launch_bounds__(32 * CB, CB <= 4 ? 2 : 1)
                  s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
         }
       }
+    }
+    // fix-up: the nodes of this tile that sit on a material interface, one per thread, shared evenly by the warps
+    // (the brick holds all the p values they need; their row blocks come from the L1-resident table)
+    for (int f = f0 + w * 32 + lane; f < f1; f += 32 * CB) {
+      const int2 e = __ldg(&ti.fix[f]);
+      const int lx = e.x & 0xff, fy = (e.x >> 8) & 0xf, fz = (e.x >> 12) & 0xf;
+      const double2 *a2 = reinterpret_cast<const double2 *>(V.rows + (size_t)e.y * RB_LEN);
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll 3
+      for (int row = 0; row < 9; ++row) {
+        const int dk = row / 3, dj = row - dk * 3;
+        const int rb = ((fz + dk) * (TILE_Y + 2) + (fy + dj)) * pitch + lx;
+#pragma unroll
+        for (int di = 0; di < 3; ++di) {
+          double av[10];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const double2 v = __ldg(a2 + (row * 3 + di) * (RB_NBR / 2) + q);
+            av[2 * q] = v.x;
+            av[2 * q + 1] = v.y;
+          }
+          const double px = s_brick[rb + di], py = s_brick[BRICK_ROWS * pitch + rb + di],
+                       pz = s_brick[2 * BRICK_ROWS * pitch + rb + di];
+          y0 += av[0] * px;
+          y0 += av[1] * py;
+          y0 += av[2] * pz;
+          y1 += av[3] * px;
+          y1 += av[4] * py;
+          y1 += av[5] * pz;
+          y2 += av[6] * px;
+          y2 += av[7] * py;
+          y2 += av[8] * pz;
+        }
+      }
+      const int n = nfix0 + fz * P.nxny + fy * P.nx + lx;
+      const int cb0 = ((fz + 1) * (TILE_Y + 2) + (fy + 1)) * pitch + lx + 1;
+      Ap[n] = y0;
+      Ap[npad + n] = y1;
+      Ap[2 * npad + n] = y2;
+      red += s_brick[cb0] * y0 + s_brick[BRICK_ROWS * pitch + cb0] * y1 + s_brick[2 * BRICK_ROWS * pitch + cb0] * y2;
     }
     __syncwarp();
 
@@ -1729,7 +1781,9 @@ struct mgpu_ctx {
   int cg_op = OP_SLOT;    // operator of the DPCG solve in flight (set by mgpu_cg_init)
   int nrows = 0;
   TileInfo tile{};        // tiled implicit SpMV (k_spmv_dot_tile)
-  int *d_chunk_id = nullptr;
+  int *d_chunk_id = nullptr, *d_chunk_pure = nullptr, *d_fix_ptr = nullptr;
+  int2 *d_fix = nullptr;
+  int nfix = 0;           // interior nodes whose row block is not a pure-material one (fix-up list of the TMA kernel)
   int tile_smem = 0;
   int imp_kernel = 1;     // 2 tiled + TMA (default when nx is even), 1 tiled + cp.async, 0 simple (MICROPP_IMP_KERNEL)
   CUtensorMap tmap_p;     // V.p as a rank-5 tensor (x, y, z, component, slot)
@@ -2172,6 +2226,51 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
             if (rowid[m0 + t] != id) id = -1;
           chunk_id[((size_t)kk * P.niy + jj) * ti.nchunk + cc] = id;
         }
+    {
+      const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+      std::vector<int> chunk_pure(chunk_id.size(), 0), fix_ptr(ntiles + 1, 0);
+      std::vector<int2> fix;
+      for (int tz = 0; tz < ti.tiles_z; ++tz)
+        for (int ty = 0; ty < ti.tiles_y; ++ty)
+          for (int tx = 0; tx < ti.tiles_x; ++tx) {
+            const int tile = (tz * ti.tiles_y + ty) * ti.tiles_x + tx;
+            fix_ptr[tile] = (int)fix.size();
+            for (int rz = 0; rz < TILE_Z; ++rz)
+              for (int ry = 0; ry < TILE_Y; ++ry)
+                for (int wq = 0; wq < ti.cb; ++wq) {
+                  const int kk = tz * TILE_Z + rz, jj = ty * TILE_Y + ry, cc = tx * ti.cb + wq;
+                  if (kk >= P.niz || jj >= P.niy || cc >= ti.nchunk) continue;
+                  const int m0 = (kk * P.niy + jj) * P.nix + cc * 8, nv = std::min(8, P.nix - cc * 8);
+                  int cnt[3] = {0, 0, 0};
+                  for (int t = 0; t < nv; ++t)
+                    if (rowid[m0 + t] < 3) cnt[rowid[m0 + t]]++;
+                  int pure = 0;
+                  for (int q = 1; q < 3; ++q)
+                    if (cnt[q] > cnt[pure]) pure = q;
+                  int mask = 0;
+                  for (int t = 0; t < nv; ++t)
+                    if (rowid[m0 + t] != pure) {
+                      mask |= 1 << t;
+                      int2 e;
+                      e.x = (wq * 8 + t) | (ry << 8) | (rz << 12);
+                      e.y = rowid[m0 + t];
+                      fix.push_back(e);
+                    }
+                  chunk_pure[((size_t)kk * P.niy + jj) * ti.nchunk + cc] = pure | (mask << 8);
+                }
+          }
+      fix_ptr[ntiles] = (int)fix.size();
+      c->nfix = (int)fix.size();
+      CK(cudaMalloc(&c->d_chunk_pure, sizeof(int) * chunk_pure.size()));
+      CK(cudaMemcpy(c->d_chunk_pure, chunk_pure.data(), sizeof(int) * chunk_pure.size(), cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&c->d_fix_ptr, sizeof(int) * fix_ptr.size()));
+      CK(cudaMemcpy(c->d_fix_ptr, fix_ptr.data(), sizeof(int) * fix_ptr.size(), cudaMemcpyHostToDevice));
+      CK(cudaMalloc(&c->d_fix, sizeof(int2) * std::max<size_t>(fix.size(), 1)));
+      if (!fix.empty()) CK(cudaMemcpy(c->d_fix, fix.data(), sizeof(int2) * fix.size(), cudaMemcpyHostToDevice));
+      ti.chunk_pure = c->d_chunk_pure;
+      ti.fix_ptr = c->d_fix_ptr;
+      ti.fix = c->d_fix;
+    }
     CK(cudaMalloc(&c->d_chunk_id, sizeof(int) * chunk_id.size()));
     CK(cudaMemcpy(c->d_chunk_id, chunk_id.data(), sizeof(int) * chunk_id.size(), cudaMemcpyHostToDevice));
     ti.chunk_id = c->d_chunk_id;
@@ -2258,6 +2357,9 @@ void mgpu_destroy(mgpu_ctx *c) {
   if (c->V.rkinv) cudaFree((void *)c->V.rkinv);
   if (c->V.rowid) cudaFree((void *)c->V.rowid);
   if (c->d_chunk_id) cudaFree(c->d_chunk_id);
+  if (c->d_chunk_pure) cudaFree(c->d_chunk_pure);
+  if (c->d_fix_ptr) cudaFree(c->d_fix_ptr);
+  if (c->d_fix) cudaFree(c->d_fix);
   cudaFree(c->T.state);
   cudaFree((void *)c->T.vars_old);
   cudaFree((void *)c->T.vars_new);
@@ -2472,6 +2574,7 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
 }
 int mgpu_implicit(const mgpu_ctx *c) { return c->implicit ? 1 : 0; }
 int mgpu_implicit_rows(const mgpu_ctx *c) { return c->nrows; }
+int mgpu_implicit_fix_nodes(const mgpu_ctx *c) { return c->nfix; }
 
 // the implicit SpMV kernel a request resolves to: 0 simple, 1 tiled (cp.async), 2 tiled (TMA)
 static int imp_kernel_of(const mgpu_ctx *c, int kern) {
