@@ -125,6 +125,8 @@ void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
 void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);
 void mgpu_ave_stress(mgpu_ctx *, int which_list, int n);
 void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);
+/* calc_fields (src/average.cpp:85-112) of the RVE staged in `slot`: element averages, [nelem][6] each (host) */
+void mgpu_elem_fields(mgpu_ctx *, int slot, double ivol, double *elem_strain, double *elem_stress);
 /* compaction: list_out <- entries of list_in whose (mode 0: nr_active, 1: cg_active) flag is set; returns count (syncs) */
 int mgpu_compact(mgpu_ctx *, int list_in, int n_in, int list_out, int mode);
 
@@ -166,6 +168,8 @@ void mgpu_timer_start(mgpu_ctx *);
 float mgpu_timer_stop(mgpu_ctx *); /* ms on the context stream (syncs) */
 /* isolated SpMV micro-benchmark on the first n slots of the pool (matrix contents as they are) */
 float mgpu_bench_spmv(mgpu_ctx *, int n, int iters);
+/* same for the implicit elastic operator; kern as in mgpu_apply_operator (2 = context default, 10 + v = TMA variant v) */
+float mgpu_bench_imp_spmv(mgpu_ctx *, int n, int iters, int kern);
 
 #ifdef __cplusplus
 }

@@ -199,6 +199,8 @@ MPP_SPEC int micropp<3>::get_non_linear_gps(void) const;
 MPP_SPEC int micropp<3>::get_cost(int gp_id) const;
 MPP_SPEC bool micropp<3>::has_converged(int gp_id) const;
 MPP_SPEC bool micropp<3>::has_subiterated(int gp_id) const;
+MPP_SPEC void micropp<3>::calc_fields(double *u, double *vars_old);
+MPP_SPEC void micropp<3>::write_vtu(double *u, double *vars_old, const char *filename);
 MPP_SPEC void micropp<3>::output(int gp_id, const char *filename);
 MPP_SPEC void micropp<3>::output2(const int gp_id, const int elem_global, const int time_step);
 MPP_SPEC void micropp<3>::write_restart(const int restart_id) const;

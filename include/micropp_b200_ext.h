@@ -91,6 +91,8 @@ void micropp3x_prof_read(struct micropp3 *self, double *out6, int reset);
 double micropp3x_last_homogenize_ms(const struct micropp3 *self);
 unsigned long long micropp3x_launch_count(const struct micropp3 *self);
 double micropp3x_bench_spmv(struct micropp3 *self, int nslots, int iters); /* ms per launch */
+/* implicit elastic operator; kern: 2 = the context's kernel, 10 + v = TMA variant v (0 shared-memory rows, v >= 1 kernel-parameter rows) */
+double micropp3x_bench_imp_spmv(struct micropp3 *self, int nslots, int iters, int kern);
 
 #ifdef __cplusplus
 }

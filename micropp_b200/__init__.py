@@ -92,6 +92,8 @@ def load():
         "micropp3_write_restart": (None, [H, C.c_int]),
         "micropp3_read_restart": (None, [H, C.c_int]),
         "micropp3_print_info": (None, [H]),
+        "micropp3_output": (None, [H, C.c_int, C.c_char_p]),
+        "micropp3_output2": (None, [H, C.c_int, C.c_int, C.c_int]),
         "micropp3_set_strains": (None, [H, _dp]),
         "micropp3_get_stresses": (None, [H, _dp]),
         "micropp3_get_ctans": (None, [H, _dp]),
@@ -121,6 +123,7 @@ def load():
         "micropp3x_last_homogenize_ms": (C.c_double, [H]),
         "micropp3x_launch_count": (C.c_ulonglong, [H]),
         "micropp3x_bench_spmv": (C.c_double, [H, C.c_int, C.c_int]),
+        "micropp3x_bench_imp_spmv": (C.c_double, [H, C.c_int, C.c_int, C.c_int]),
         "material_set": (None, [C.POINTER(MaterialBase), C.c_int] + [C.c_double] * 5),
         "mgpu_device_count": (C.c_int, []),
     }
@@ -268,6 +271,14 @@ class Micropp3:
     def print_info(self):
         self.lib.micropp3_print_info(C.byref(self.h))
 
+    def output(self, gp, filename):
+        """Write <filename>.vtu for one Gauss point (src/output.cpp:30-41)."""
+        self.lib.micropp3_output(C.byref(self.h), int(gp), str(filename).encode())
+
+    def output2(self, gp, elem_global, time_step):
+        """Write micropp-<elem_global>-<time_step>.vtu into the working directory (src/output.cpp:44-69)."""
+        self.lib.micropp3_output2(C.byref(self.h), int(gp), int(elem_global), int(time_step))
+
     # ---- inspection -----------------------------------------------------------------------------
     def wave_size(self):
         return int(self.lib.micropp3x_wave_size(C.byref(self.h)))
@@ -361,6 +372,10 @@ class Micropp3:
 
     def bench_spmv(self, nslots, iters=20):
         return float(self.lib.micropp3x_bench_spmv(C.byref(self.h), int(nslots), int(iters)))
+
+    def bench_imp_spmv(self, nslots, iters=20, kern=2):
+        """ms per application of the implicit elastic operator on `nslots` RVEs (kern: 2 context default, 10+v TMA variant v)."""
+        return float(self.lib.micropp3x_bench_imp_spmv(C.byref(self.h), int(nslots), int(iters), int(kern)))
 
 
 # ---- free functions of the ELL API ----------------------------------------------------------------------

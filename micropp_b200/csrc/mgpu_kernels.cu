@@ -1376,6 +1376,227 @@ __global__ void __launch_bounds__(32 * CB, CB <= 4 ? 2 : 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_spmv_dot_tmac: k_spmv_dot_tma with the three pure-material row blocks passed BY VALUE as a __grid_constant__
+// kernel parameter (6.5 KB in the constant bank).  ncu of k_spmv_dot_tma<4> (profiles/r01c_*): the FP64 pipe is 40 %
+// busy; per neighbour row a warp issues 15 LDS.128 for p plus 15 LDS.128 for the (warp-uniform) row block, holds
+// 221 registers and runs 2 warps per scheduler.  Here the row-block values are operands of the DFMA itself (uniform
+// register loaded by LDCU from the constant bank: no LSU/shared-memory traffic, no vector registers), the material is
+// a compile-time constant of an unrolled three-way branch (lanes of a warp whose chunks sit in different materials
+// take their branches one after the other), which halves the shared-memory wavefronts and brings the kernel under
+// 128 registers.  Template parameters select the variants measured on the B200 (tools/bench_imp_spmv.py):
+//   NSTAGE  1: one brick per block, more resident blocks hide the TMA latency; 2: two-stage mbarrier pipeline;
+//   MINB    resident blocks per SM the register allocation is bounded for;
+//   RU      unroll factor of the loop over the 9 neighbour rows.
+// Arithmetic (FMA order per accumulator) is that of k_spmv_dot / k_spmv_dot_tma: Ap is bit-identical.
+// ------------------------------------------------------------------------------------------------
+struct PureRows {
+  double a[3 * RB_LEN];
+};
+
+template <int MAT, int RU, int PITCH>
+__device__ __forceinline__ void tile_rows_apply_const(const PureRows &R, const double *__restrict__ brick, int bx0,
+                                                      int ry, int rz, double (&acc)[8][3]) {
+#pragma unroll RU
+  for (int row = 0; row < 9; ++row) {
+    const int dk = row / 3, dj = row - dk * 3;  // 0..2 (offset + 1)
+    const int rbase = ((rz + dk) * (TILE_Y + 2) + (ry + dj)) * PITCH + bx0;
+    double pv[3][10];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double2 *s2 = reinterpret_cast<const double2 *>(brick + d * (BRICK_ROWS * PITCH) + rbase);
+#pragma unroll
+      for (int h = 0; h < 5; ++h) {
+        const double2 v = s2[h];
+        pv[d][2 * h] = v.x;
+        pv[d][2 * h + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const double *a = &R.a[MAT * RB_LEN + (row * 3 + di) * RB_NBR];
+#pragma unroll
+      for (int fj = 0; fj < 3; ++fj) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const double pval = pv[fj][t + di];
+          acc[t][0] += a[fj] * pval;
+          acc[t][1] += a[3 + fj] * pval;
+          acc[t][2] += a[6 + fj] * pval;
+        }
+      }
+    }
+  }
+}
+
+template <int CB, int NSTAGE, int MINB, int RU>
+__global__ void __launch_bounds__(32 * CB, MINB)
+    k_spmv_dot_tmac(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V, TileInfo ti,
+                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PureRows R, int ntl, int rs,
+                    int force) {
+  extern __shared__ unsigned char s_raw[];
+  constexpr int pitch = 8 * CB + 2;
+  constexpr int BRICK = 3 * BRICK_ROWS * pitch;  // doubles
+  constexpr int STAGE_BYTES = (BRICK * 8 + 127) / 128 * 128;
+  __shared__ uint64_t s_full[NSTAGE];
+  __shared__ int s_slot[TMA_MAX_RS];
+  __shared__ int s_done[NSTAGE];
+  unsigned char *s_base = s_raw + ((128u - ((unsigned)__cvta_generic_to_shared(s_raw) & 127u)) & 127u);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+  const int tile0 = blockIdx.x * ntl;
+  const int nitems = min(ntl, ntiles - tile0) * rs;
+
+  if ((int)threadIdx.x < rs) {
+    const int yy = (int)blockIdx.y * rs + (int)threadIdx.x + L.yoff;
+    const int cnt = L.dcount ? min(*L.dcount, n_list + L.yoff) : n_list + L.yoff;
+    int slot = yy < cnt ? L.list[yy] : -1;
+    if (slot >= 0 && !force && !T.state[slot].cg_active) slot = -1;
+    s_slot[threadIdx.x] = slot;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NSTAGE; ++q) {
+      s_done[q] = 0;
+      mbar_init(&s_full[q], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  auto next_active = [&](int i) {
+    while (i < nitems && s_slot[i % rs] < 0) ++i;
+    return i;
+  };
+  auto issue = [&](int item, int stage) {  // one thread
+    const int tile = tile0 + item / rs, slot = s_slot[item % rs];
+    const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+    mbar_expect_tx(&s_full[stage], BRICK * 8);
+    tma_load_5d(s_base + stage * STAGE_BYTES, &tmap, &s_full[stage], tx * 8 * CB, ty * TILE_Y, tz * TILE_Z, 0, slot);
+  };
+
+  const int ry = lane & 7, rz = lane >> 3;
+  const size_t npad = P.nn_pad;
+  int cur = next_active(0), k = 0;
+  if (threadIdx.x == 0) {
+    int it = cur;
+#pragma unroll
+    for (int q = 0; q < NSTAGE; ++q) {
+      if (it < nitems) issue(it, q);
+      it = it < nitems ? next_active(it + 1) : nitems;
+    }
+  }
+  int cur_tile = -1, pure = 0, keep = 0, n0 = 0, f0 = 0, f1 = 0, nfix0 = 0;
+  bool work = false;
+  while (cur < nitems) {
+    const int nxt = next_active(cur + 1);
+    const int stage = k % NSTAGE;
+    const int tile = tile0 + cur / rs, slot = s_slot[cur % rs];
+    if (tile != cur_tile) {
+      cur_tile = tile;
+      const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+      const int c = tx * CB + w, jj = ty * TILE_Y + ry, kk = tz * TILE_Z + rz;
+      work = c < ti.nchunk && jj < P.niy && kk < P.niz;
+      const int info = work ? __ldg(&ti.chunk_pure[(kk * P.niy + jj) * ti.nchunk + c]) : 0;
+      pure = info & 0xff;
+      const int ii0 = c * 8;
+      const int nvalid = min(8, P.nix - ii0);
+      keep = work ? (((1 << nvalid) - 1) & ~(info >> 8)) : 0;  // nodes this thread stores itself
+      n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
+      f0 = __ldg(&ti.fix_ptr[tile]);
+      f1 = __ldg(&ti.fix_ptr[tile + 1]);
+      nfix0 = (ty * TILE_Y + 1) * P.nx + (tz * TILE_Z + 1) * P.nxny + tx * 8 * CB + 1;  // node of tile position 0
+    }
+    const double *s_brick = reinterpret_cast<const double *>(s_base + stage * STAGE_BYTES);
+    mbar_wait(&s_full[stage], (k / NSTAGE) & 1);
+
+    double red = 0.0;
+    double *Ap = V.Ap + (size_t)slot * V.vstride;
+    if (work) {
+      double acc[8][3];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+      if (pure == 0)
+        tile_rows_apply_const<0, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
+      else if (pure == 1)
+        tile_rows_apply_const<1, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
+      else
+        tile_rows_apply_const<2, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
+      const int cbase = ((rz + 1) * (TILE_Y + 2) + (ry + 1)) * pitch + 8 * w + 1;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if ((keep >> t) & 1) {
+          Ap[n0 + t] = acc[t][0];
+          Ap[npad + n0 + t] = acc[t][1];
+          Ap[2 * npad + n0 + t] = acc[t][2];
+          red += s_brick[cbase + t] * acc[t][0] + s_brick[BRICK_ROWS * pitch + cbase + t] * acc[t][1] +
+                 s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
+        }
+      }
+    }
+    // fix-up: the nodes of this tile that sit on a material interface, one per thread (as in k_spmv_dot_tma)
+    for (int f = f0 + w * 32 + lane; f < f1; f += 32 * CB) {
+      const int2 e = __ldg(&ti.fix[f]);
+      const int lx = e.x & 0xff, fy = (e.x >> 8) & 0xf, fz = (e.x >> 12) & 0xf;
+      const double2 *a2 = reinterpret_cast<const double2 *>(V.rows + (size_t)e.y * RB_LEN);
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll 3
+      for (int row = 0; row < 9; ++row) {
+        const int dk = row / 3, dj = row - dk * 3;
+        const int rb = ((fz + dk) * (TILE_Y + 2) + (fy + dj)) * pitch + lx;
+#pragma unroll
+        for (int di = 0; di < 3; ++di) {
+          double av[10];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const double2 v = __ldg(a2 + (row * 3 + di) * (RB_NBR / 2) + q);
+            av[2 * q] = v.x;
+            av[2 * q + 1] = v.y;
+          }
+          const double px = s_brick[rb + di], py = s_brick[BRICK_ROWS * pitch + rb + di],
+                       pz = s_brick[2 * BRICK_ROWS * pitch + rb + di];
+          y0 += av[0] * px;
+          y0 += av[1] * py;
+          y0 += av[2] * pz;
+          y1 += av[3] * px;
+          y1 += av[4] * py;
+          y1 += av[5] * pz;
+          y2 += av[6] * px;
+          y2 += av[7] * py;
+          y2 += av[8] * pz;
+        }
+      }
+      const int n = nfix0 + fz * P.nxny + fy * P.nx + lx;
+      const int cb0 = ((fz + 1) * (TILE_Y + 2) + (fy + 1)) * pitch + lx + 1;
+      Ap[n] = y0;
+      Ap[npad + n] = y1;
+      Ap[2 * npad + n] = y2;
+      red += s_brick[cb0] * y0 + s_brick[BRICK_ROWS * pitch + cb0] * y1 + s_brick[2 * BRICK_ROWS * pitch + cb0] * y2;
+    }
+    __syncwarp();
+
+    // stage sign-off; the last warp re-arms the stage with the NSTAGE-th active item after this one
+    if (lane == 0) {
+      const int done = atomicAdd(&s_done[stage], 1);
+      if (done == CB - 1) {
+        s_done[stage] = 0;
+        int after = nxt;
+#pragma unroll
+        for (int q = 1; q < NSTAGE; ++q) after = after < nitems ? next_active(after + 1) : nitems;
+        if (after < nitems) {
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          issue(after, stage);
+        }
+      }
+    }
+    red = warp_sum(red);
+    if (lane == 0) T.partial[((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max + tile * CB + w] = red;
+    cur = nxt;
+    ++k;
+  }
+}
+
 __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, int n, int d) {
   int i, j, k;
   node_ijk(P, n, i, j, k);
@@ -1671,6 +1892,44 @@ __global__ void __launch_bounds__(NT)
   if (__syncthreads_or(nl) && threadIdx.x == 0) atomicOr(&st->nl_flag, 1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// calc_fields (src/average.cpp:85-112): element averages of strain and stress for the VTU output; thread per
+// element, out[e*6+v] (strain) and out[6*nelem + e*6+v] (stress) in the reference's element-major layout
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+    k_elem_fields(const __grid_constant__ MeshConst P, int slot, SlotTables T, const double *__restrict__ u_pool,
+                  size_t vstride, const int *__restrict__ elem_type, double ivol, double *__restrict__ out) {
+  const double *u = u_pool + (size_t)slot * vstride;
+  const double *vars = T.vars_old[slot];
+  const int e = blockIdx.x * NT + threadIdx.x;
+  if (e >= P.nelem) return;
+  const int ez = e / (P.nex * P.ney);
+  const int r = e - ez * P.nex * P.ney;
+  const int ey = r / P.nex, ex = r - ey * P.nex;
+  double ue[24];
+  gather_ue(P, u, ex, ey, ez, ue);
+  const mpp_material m = P.mat[__ldg(&elem_type[e])];
+  const int nv = mat_nvar(m.type);
+  double ea[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, sa[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int gp = 0; gp < 8; ++gp) {
+    double eps[6], sig[6], vbuf[7];
+    gp_strain(P.dsh[gp], ue, eps);
+    const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+    mat_stress(m, eps, v, sig);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      ea[q] = add_(ea[q], mul_(eps[q], P.wg));
+      sa[q] = add_(sa[q], mul_(sig[q], P.wg));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    out[(size_t)e * 6 + q] = mul_(ea[q], ivol);
+    out[(size_t)(P.nelem + e) * 6 + q] = mul_(sa[q], ivol);
+  }
+}
+
 // slab mode: scalar tails after the cross-rank all-reduce of T.red (kind: 0 rhs, 1 cg_init, 2 spmv, 3 cg_update,
 // 4 average stress)
 __global__ void k_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, int kind, int mode) {
@@ -1788,6 +2047,8 @@ struct mgpu_ctx {
   int imp_kernel = 1;     // 2 tiled + TMA (default when nx is even), 1 tiled + cp.async, 0 simple (MICROPP_IMP_KERNEL)
   CUtensorMap tmap_p;     // V.p as a rank-5 tensor (x, y, z, component, slot)
   int tma_smem = 0;
+  PureRows pure_rows;     // host copy of row blocks 0..2 (kernel parameter of k_spmv_dot_tmac)
+  int tma_variant = 0;    // 0: k_spmv_dot_tma (row blocks in shared memory); v >= 1: k_spmv_dot_tmac variant v
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
   double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
@@ -1864,6 +2125,35 @@ inline tma_kernel_t tma_kernel(int cb) {
     case 6: return k_spmv_dot_tma<6>;
     case 7: return k_spmv_dot_tma<7>;
     default: return k_spmv_dot_tma<8>;
+  }
+}
+
+// variants of k_spmv_dot_tmac (row blocks as a kernel parameter): {stages, resident blocks per SM, row unroll}
+struct TmacVariant {
+  int nstage, minb, ru;
+};
+constexpr int N_TMAC = 7;
+static const TmacVariant kTmac[N_TMAC] = {{2, 2, 1}, {2, 2, 3}, {1, 4, 1}, {1, 3, 3}, {1, 3, 1}, {2, 2, 9}, {1, 3, 9}};
+typedef void (*tmac_kernel_t)(const MeshConst, const Lst, int, SlotTables, VecPool, TileInfo, const CUtensorMap,
+                              const PureRows, int, int, int);
+template <int NS, int MB, int RU>
+inline tmac_kernel_t tmac_pick(int cb) {
+  switch (cb) {
+    case 1: return k_spmv_dot_tmac<1, NS, MB, RU>;
+    case 2: return k_spmv_dot_tmac<2, NS, MB, RU>;
+    case 3: return k_spmv_dot_tmac<3, NS, MB, RU>;
+    default: return k_spmv_dot_tmac<4, NS, MB, RU>;
+  }
+}
+inline tmac_kernel_t tmac_kernel(int variant, int cb) {  // variant 1..N_TMAC
+  switch (variant) {
+    case 1: return tmac_pick<2, 2, 1>(cb);
+    case 2: return tmac_pick<2, 2, 3>(cb);
+    case 3: return tmac_pick<1, 4, 1>(cb);
+    case 4: return tmac_pick<1, 3, 3>(cb);
+    case 5: return tmac_pick<1, 3, 1>(cb);
+    case 6: return tmac_pick<2, 2, 9>(cb);
+    default: return tmac_pick<1, 3, 9>(cb);
   }
 }
 
@@ -2195,6 +2485,8 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     V.rows = d_rows;
     V.rkinv = d_rkinv;
     V.rowid = d_rowid;
+    memset(&c->pure_rows, 0, sizeof(PureRows));
+    CK(cudaMemcpy(c->pure_rows.a, d_rows, sizeof(double) * RB_LEN * std::min(c->nrows, 3), cudaMemcpyDeviceToHost));
 
     // tiling of k_spmv_dot_tile: chunks of 8 x-adjacent interior nodes, cb chunks (warps) per block
     TileInfo &ti = c->tile;
@@ -2297,6 +2589,13 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
           c->imp_kernel = 2;
           c->tma_smem = 2 * ((c->tile_smem + 127) / 128 * 128) + 128;
           CK(cudaFuncSetAttribute(tma_kernel(ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize, c->tma_smem));
+          if (ti.cb <= 4) {
+            for (int v = 1; v <= N_TMAC; ++v)
+              CK(cudaFuncSetAttribute(tmac_kernel(v, ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kTmac[v - 1].nstage * ((c->tile_smem + 127) / 128 * 128) + 128));
+            if (const char *env = getenv("MICROPP_TMA_VARIANT"))
+              c->tma_variant = std::min(std::max(atoi(env), 0), N_TMAC);
+          }
         } else {
           fprintf(stderr, "micropp-b200: cuTensorMapEncodeTiled failed (%d); using the cp.async tiled kernel\n", (int)r);
         }
@@ -2592,11 +2891,24 @@ static int imp_fold_count(const mgpu_ctx *c) {
 static void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
   const TileInfo &ti = c->tile;
   const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
+  // kern 2: the context's TMA kernel; kern 10 + v: TMA variant v (0 = k_spmv_dot_tma, v >= 1 = k_spmv_dot_tmac)
+  int variant = c->tma_variant;
+  if (kern >= 10) {
+    variant = std::min(kern - 10, ti.cb <= 4 ? N_TMAC : 0);
+    kern = 2;
+  }
   kern = imp_kernel_of(c, kern);
   if (kern == 2) {
     const int rs = std::min(TMA_MAX_RS, n), ntl = rs >= 4 ? 1 : TMA_MAX_RS / rs;
-    tma_kernel(ti.cb)<<<dim3((ntiles + ntl - 1) / ntl, (n + rs - 1) / rs), 32 * ti.cb, c->tma_smem, c->stream>>>(
-        c->mc, lst_of(c, l), n, c->T, c->V, ti, c->tmap_p, ntl, rs, force);
+    const dim3 grid((ntiles + ntl - 1) / ntl, (n + rs - 1) / rs);
+    if (variant >= 1) {
+      const int smem = kTmac[variant - 1].nstage * ((c->tile_smem + 127) / 128 * 128) + 128;
+      tmac_kernel(variant, ti.cb)<<<grid, 32 * ti.cb, smem, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, ti,
+                                                                        c->tmap_p, c->pure_rows, ntl, rs, force);
+    } else {
+      tma_kernel(ti.cb)<<<grid, 32 * ti.cb, c->tma_smem, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, ti,
+                                                                     c->tmap_p, ntl, rs, force);
+    }
     // p.Ap: one warp per slot folds the per-(tile, warp) partials in a fixed order and runs the scalar tail
     k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, ntiles * ti.cb, force);
     c->launches++;
@@ -2669,6 +2981,21 @@ void mgpu_vars_new(mgpu_ctx *c, int l, int n, int write) {
   k_vars_new<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride,
                                                    c->d_elem_type, write);
   CK(cudaGetLastError());
+}
+// element-averaged strain / stress of the RVE staged in `slot` (host arrays of 6*nelem doubles each)
+void mgpu_elem_fields(mgpu_ctx *c, int slot, double ivol, double *elem_strain, double *elem_stress) {
+  CK(cudaSetDevice(c->device));
+  const size_t len = (size_t)c->mc.nelem * 6;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * 2 * len));
+  c->launches++;
+  k_elem_fields<<<(c->mc.nelem + NT - 1) / NT, NT, 0, c->stream>>>(c->mc, slot, c->T, c->V.u, c->V.vstride,
+                                                                  c->d_elem_type, ivol, d);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(elem_strain, d, sizeof(double) * len, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(elem_stress, d + len, sizeof(double) * len, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
 }
 void mgpu_clear_nl_flags(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
@@ -3001,6 +3328,27 @@ float mgpu_bench_spmv(mgpu_ctx *c, int n, int iters) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c->t0, c->t1));
   c->launches += iters + 2;
+  return ms / iters;
+}
+
+// isolated micro-benchmark of the implicit-operator SpMV (+ its p.Ap fold) on the first n slots; kern as in
+// mgpu_apply_operator (2 = the context's kernel, 10 + v = TMA variant v).  p as it stands in the pool.
+float mgpu_bench_imp_spmv(mgpu_ctx *c, int n, int iters, int kern) {
+  CK(cudaSetDevice(c->device));
+  if (!c->implicit) return -1.f;
+  n = std::min(n, c->W);
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) ids[i] = i;
+  mgpu_set_list(c, 5, n, ids.data());
+  for (int w = 0; w < 2; ++w) launch_imp_spmv(c, 5, n, 1, kern);
+  CK(cudaEventRecord(c->t0, c->stream));
+  for (int it = 0; it < iters; ++it) launch_imp_spmv(c, 5, n, 1, kern);
+  CK(cudaEventRecord(c->t1, c->stream));
+  CK(cudaEventSynchronize(c->t1));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->t0, c->t1));
+  c->launches += 2 * (iters + 2);
   return ms / iters;
 }
 

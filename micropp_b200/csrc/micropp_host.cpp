@@ -749,19 +749,140 @@ void micropp<3>::get_stress(int gp, const double eps[nvoi], const double *vars_o
   get_material(e)->get_stress(eps, stress_gp, vars);
 }
 
+// ------------------------------------------------------------------------------------------------
+// VTU output (src/output.cpp:30-213): the GP's u_k and vars_n come back from HBM in the reference's layouts, the
+// element averages are computed on the device (k_elem_fields), the file is written in the reference's format.
+// ------------------------------------------------------------------------------------------------
+template <>
+void micropp<3>::calc_fields(double *u, double *vars_old) {
+  stage_begin(engine, u, vars_old);
+  mgpu_elem_fields(engine->ctx, kSlot0, ivol, elem_strain, elem_stress);
+}
+
+namespace {
+// one <DataArray> of the ASCII VTU file; `body` writes the values
+template <class F>
+void vtu_array(std::ostream &os, const char *type, const char *name, int ncomp, F body, const char *type_pad = "",
+               const char *close_pad = "") {
+  os << "<DataArray type=\"" << type << "\"" << type_pad << " Name=\"" << name << "\" NumberOfComponents=\"" << ncomp
+     << "\" format=\"ascii\"" << close_pad << ">" << endl;
+  body();
+}
+}  // namespace
+
+template <>
+void micropp<3>::write_vtu(double *u, double *vars_old, const char *filename) {
+  ofstream os(std::string(filename) + ".vtu");
+  os << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
+     << "<UnstructuredGrid>\n<Piece NumberOfPoints=\"" << nn << "\" NumberOfCells=\"" << nelem << "\">\n<Points>\n"
+     << "<DataArray type=\"Float64\" Name=\"Position\" NumberOfComponents=\"3\" format=\"ascii\">" << endl;
+  os << scientific;
+  for (int n = 0; n < nn; ++n) {
+    const int i = n % nx, j = (n / nx) % ny, k = n / (nx * ny);
+    os << i * dx << " " << j * dy << " " << k * dz << " \n";
+  }
+  os << "</DataArray>\n</Points>\n<Cells>\n" << endl;
+
+  vtu_array(os, "Int32", "connectivity", 1, [&] {
+    for (int e = 0; e < nelem; ++e) {
+      const int ex = e % nex, ey = (e / nex) % ney, ez = e / (nex * ney);
+      int nodes[8];
+      get_elem_nodes(nodes, nx, ny, ex, ey, ez);
+      for (int a = 0; a < npe; ++a) os << nodes[a] << ' ';
+      os << "\n";
+    }
+    os << "</DataArray>" << endl;
+  });
+  vtu_array(os, "Int32", "offsets", 1, [&] {
+    for (int e = 1; e <= nelem; ++e) os << e * npe << " ";
+    os << "\n</DataArray>" << endl;
+  });
+  vtu_array(os, "UInt8", "types", 1, [&] {
+    for (int e = 0; e < nelem; ++e) os << 12 << " ";  // VTK_HEXAHEDRON
+    os << "\n</DataArray>" << endl;
+  }, " ");
+  os << "</Cells>" << endl;
+
+  os << "<PointData Vectors=\"displ\" >" << endl;
+  vtu_array(os, "Float64", "displ", 3, [&] {
+    for (int n = 0; n < nn; ++n) os << u[n * 3] << " " << u[n * 3 + 1] << " " << u[n * 3 + 2] << " \n";
+    os << "</DataArray>" << endl;
+  }, "", " ");
+  os << "</PointData>" << endl;
+
+  os << "<CellData>" << endl;
+  auto per_elem6 = [&](const double *f) {
+    for (int e = 0; e < nelem; ++e) {
+      for (int v = 0; v < nvoi; ++v) os << f[e * nvoi + v] << " ";
+      os << "\n";
+    }
+    os << "</DataArray>\n";
+  };
+  vtu_array(os, "Float64", "strain", nvoi, [&] { per_elem6(elem_strain); });
+  vtu_array(os, "Float64", "stress", nvoi, [&] { per_elem6(elem_stress); });
+  vtu_array(os, "Int32", "elem_type", 1, [&] {
+    for (int e = 0; e < nelem; ++e) os << elem_type[e] << " ";
+    os << "\n</DataArray>" << endl;
+  });
+  // Gauss-point means of internal variables (0 without a state).  "plasticity" keeps the reference's expression:
+  // s = sum of the squared plastic strains, reported value (s + sqrt(s)) / 8 (src/output.cpp:160-168)
+  auto var_mean = [&](const char *name, auto per_element) {
+    vtu_array(os, "Float64", name, 1, [&] {
+      for (int e = 0; e < nelem; ++e) os << per_element(e) / npe << " ";
+      os << "\n</DataArray>" << endl;
+    });
+  };
+  auto gp_sum = [&](int e, int v) {
+    double s = 0.0;
+    if (vars_old)
+      for (int gp = 0; gp < npe; ++gp) s += vars_old[intvar_ix(e, gp, v)];
+    return s;
+  };
+  var_mean("plasticity", [&](int e) {
+    double s = 0.0;
+    if (vars_old)
+      for (int gp = 0; gp < npe; ++gp)
+        for (int v = 0; v < nvoi; ++v) s += vars_old[intvar_ix(e, gp, v)] * vars_old[intvar_ix(e, gp, v)];
+    return s + sqrt(s);
+  });
+  var_mean("damage_e", [&](int e) { return gp_sum(e, 0); });
+  var_mean("damage_D", [&](int e) { return gp_sum(e, 1); });
+  var_mean("hardening", [&](int e) { return gp_sum(e, 6); });
+  os << "</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>" << endl;
+}
+
+namespace {
+// u_k and vars_n of a GP in the reference's host layouts (vars empty = the reference's nullptr)
+void fetch_gp_state(mpp_engine *engine, const gp_t<3> &g, int nndim, int nvars, std::vector<double> &u,
+                    std::vector<double> &vars) {
+  u.assign(nndim, 0.0);
+  vars.clear();
+  if (g.fe_index < 0) return;
+  mgpu_gp_get_u(engine->ctx, g.fe_index, 1, u.data());
+  if (g.allocated) {
+    vars.resize(nvars);
+    mgpu_gp_get_vars(engine->ctx, g.fe_index, 0, vars.data());
+  }
+}
+}  // namespace
+
 template <>
 void micropp<3>::output(int gp_id, const char *filename) {
-  (void)gp_id;
-  cerr << "micropp-b200: VTU output (" << filename << ") is outside the B200 hot-path scope of this build" << endl;
+  assert(gp_id >= 0 && gp_id < ngp);
+  std::vector<double> u, vars;
+  fetch_gp_state(engine, gp_list[gp_id], nndim, nvars, u, vars);
+  double *vp = vars.empty() ? nullptr : vars.data();
+  calc_fields(u.data(), vp);
+  write_vtu(u.data(), vp, filename);
 }
+
+// writes "micropp-<elem_global>-<time_step>.vtu" (src/output.cpp:44-69)
 template <>
 void micropp<3>::output2(const int gp_id, const int elem_global, const int time_step) {
-  (void)gp_id;
-  cerr << "micropp-b200: VTU output (micropp-" << elem_global << "-" << time_step
-       << ") is outside the B200 hot-path scope of this build" << endl;
+  std::stringstream name;
+  name << "micropp-" << elem_global << "-" << time_step;
+  output(gp_id, name.str().c_str());
 }
-
-
 
 // ================================================================================================
 // access for the C-ABI extension layer
@@ -905,6 +1026,9 @@ double micropp3x_apply_operator(micropp3 *s, const double *p, double *Ap, int op
 }
 double micropp3x_bench_spmv(micropp3 *s, int nslots, int iters) {
   return mgpu_bench_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters);
+}
+double micropp3x_bench_imp_spmv(micropp3 *s, int nslots, int iters, int kern) {
+  return mgpu_bench_imp_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters, kern);
 }
 }
 

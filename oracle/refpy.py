@@ -176,6 +176,9 @@ class RefMicropp:
     def read_restart(self, rid):
         self.lib.ref_read_restart(self.h, int(rid))
 
+    def output(self, gp, filename):
+        self.lib.ref_output(self.h, int(gp), str(filename).encode())
+
     # inspection
     def elem_type(self):
         out = np.zeros(self.nelem, dtype=np.int32)

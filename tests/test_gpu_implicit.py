@@ -132,10 +132,12 @@ def test_operator_application_three_ways(mpp, refpy, dims):
     y0, d0 = g.apply_operator(p, op=0)
     y1, d1 = g.apply_operator(p, op=3, kernel=0)
     assert np.array_equal(y0, y1) and d0 == d1
-    for kernel in (1, 2):
+    # 1 = cp.async tiles, 2 = the context's TMA kernel, 10 + v = every TMA variant (0: row blocks in shared memory,
+    # 1..7: row blocks as a kernel parameter -- k_spmv_dot_tmac with 1/2 stages, 2/3/4 blocks per SM, row unroll 1/3/9)
+    for kernel in (1, 2) + tuple(range(10, 18)):
         y2, d2 = g.apply_operator(p, op=3, kernel=kernel)
-        assert np.array_equal(y0, y2)
-        assert abs(d2 - d0) <= 1e-13 * abs(d0)
+        assert np.array_equal(y0, y2), kernel
+        assert abs(d2 - d0) <= 1e-13 * abs(d0), kernel
     r = refpy.RefMicropp(refpy.default_params(**kw))
     A = r.assembly_mat(np.zeros(g.nndim))
     yr = refpy.ell_mvp(*dims, A, p)

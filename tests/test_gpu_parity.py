@@ -326,3 +326,50 @@ def test_restart_roundtrip(mpp, refpy, tmp_path, monkeypatch):
         assert g2.is_non_linear(gp) == 1 and g3.is_non_linear(gp) == 1
         assert relerr(g2.get_stress(gp), g.get_stress(gp)) < 1e-12
         assert relerr(g3.get_stress(gp), r.get_stress(gp)) < 1e-7
+
+
+def _vtu_arrays(path):
+    """(structure, {name: values}) of an ASCII .vtu file: the text with every DataArray body blanked, and the numbers."""
+    import re
+    text = path.read_text()
+    arrays = {}
+
+    def grab(m):
+        arrays[re.search(r'Name="(\w+)"', m.group(1)).group(1)] = np.array(m.group(2).split(), dtype=np.float64)
+        return m.group(1) + "</DataArray>"
+
+    skeleton = re.sub(r"(<DataArray[^>]*>)(.*?)</DataArray>", grab, text, flags=re.S)
+    return skeleton, arrays
+
+
+@pytest.mark.parametrize("case,n,steps", [("damage_sphere", 6, 10), ("plastic_layer", 5, 3), ("elastic_sphere", 5, 1)])
+def test_vtu_output(mpp, refpy, tmp_path, case, n, steps):
+    """output() writes the reference's VTU file (src/output.cpp:30-213): same XML skeleton byte for byte, same arrays
+    (mesh/connectivity exactly; fields computed on the device by k_elem_fields within 1e-8)."""
+    kw = dict(ngp=2, lin_stress=False, calc_ctan_lin=False, nr_max_its=10)
+    g, r = pair(mpp, refpy, case, n, **kw)
+    path = load_path(2, steps, 9)
+    run_history(g, path)
+    run_history(r, path)
+    for gp in range(2):
+        g.output(gp, tmp_path / f"ours{gp}")
+        r.output(gp, tmp_path / f"ref{gp}")
+        so, ao = _vtu_arrays(tmp_path / f"ours{gp}.vtu")
+        sr, ar = _vtu_arrays(tmp_path / f"ref{gp}.vtu")
+        assert so == sr
+        assert set(ao) == set(ar) == {"Position", "connectivity", "offsets", "types", "displ", "strain", "stress",
+                                      "elem_type", "plasticity", "damage_e", "damage_D", "hardening"}
+        for name in ("Position", "connectivity", "offsets", "types", "elem_type"):
+            assert np.array_equal(ao[name], ar[name]), name
+        for name in ("displ", "strain", "stress", "plasticity", "damage_e", "damage_D", "hardening"):
+            assert ao[name].shape == ar[name].shape, name
+            assert relerr(ao[name], ar[name], floor=1e-30) < 2e-6, name  # the file holds 7 significant digits
+    # output2 names the file itself (src/output.cpp:44-69)
+    import os
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        g.output2(1, 42, 3)
+    finally:
+        os.chdir(cwd)
+    assert _vtu_arrays(tmp_path / "micropp-42-3.vtu")[1]["displ"].shape == ao["displ"].shape
