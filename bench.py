@@ -371,8 +371,8 @@ def main():
             b_alg = spmv_imp_bytes_per_rve(n)
             flops = 2.0 * 243.0 * (n - 2) ** 3
             achieved = b_alg * apps / sec / 1e9
-            name = {0: "k_spmv_dot_imp<8>", 1: "k_spmv_dot_tile", 2: "k_spmv_dot_tma"}[implicit_kernel]
-            key = "implicit_" + {0: "simple", 1: "tile", 2: "tma"}[implicit_kernel]
+            name = {0: "k_spmv_dot_imp<8>", 1: "k_spmv_dot_tile", 2: "k_spmv_dot_tma", 3: "k_spmv_dot_tmac"}[implicit_kernel]
+            key = "implicit_" + {0: "simple", 1: "tile", 2: "tma", 3: "tmac"}[implicit_kernel]
             r = {"kernel": name + " (DPCG SpMV + p.Ap on the implicit elastic operator: no matrix stream)",
                  "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                  "peak_source": peak_src, "traffic": None, "bytes_per_rve_application": b_alg,

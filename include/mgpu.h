@@ -113,7 +113,7 @@ void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_share
 int mgpu_implicit(const mgpu_ctx *);
 int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
 int mgpu_implicit_fix_nodes(const mgpu_ctx *); /* interior nodes on material interfaces (fix-up list of the TMA kernel) */
-int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 simple, 1 tiled (cp.async), 2 tiled (TMA) */
+int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 simple, 1 tiled (cp.async), 2 tiled (TMA, rows in smem), 3 tiled (TMA, rows as kernel parameter: k_spmv_dot_tmac) */
 void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitrary matrix: boundary rows read too */
@@ -122,6 +122,9 @@ void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitra
 void mgpu_apply_operator(mgpu_ctx *, int which_list, int n, int op, int imp_kernel);
 void mgpu_cg_update(mgpu_ctx *, int which_list, int n);
 void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
+/* x += alpha p of the last iteration (deferred from mgpu_cg_update to mgpu_cg_pupdate, which the last iteration
+   of a slot skips): call once after the DPCG loop, before du is used */
+void mgpu_cg_finish(mgpu_ctx *, int which_list, int n);
 void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);
 void mgpu_ave_stress(mgpu_ctx *, int which_list, int n);
 void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);
@@ -129,6 +132,7 @@ void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);
 void mgpu_elem_fields(mgpu_ctx *, int slot, double ivol, double *elem_strain, double *elem_stress);
 /* compaction: list_out <- entries of list_in whose (mode 0: nr_active, 1: cg_active) flag is set; returns count (syncs) */
 int mgpu_compact(mgpu_ctx *, int list_in, int n_in, int list_out, int mode);
+int mgpu_compact_range(mgpu_ctx *, int list_in, int off, int n_in, int list_out, int mode); /* entries [off, off+n_in) */
 
 /* One whole Newton step (assembly_mat -> DPCG as a device-driven WHILE node -> u += du -> assembly_rhs) as one
    CUDA graph over list 1 (the Newton list, whose device-side length mgpu_compact(.., 1, ..) maintains).  Returns

@@ -1377,30 +1377,50 @@ __global__ void __launch_bounds__(32 * CB, CB <= 4 ? 2 : 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_spmv_dot_tmac: k_spmv_dot_tma with the three pure-material row blocks passed BY VALUE as a __grid_constant__
-// kernel parameter (6.5 KB in the constant bank).  ncu of k_spmv_dot_tma<4> (profiles/r01c_*): the FP64 pipe is 40 %
-// busy; per neighbour row a warp issues 15 LDS.128 for p plus 15 LDS.128 for the (warp-uniform) row block, holds
-// 221 registers and runs 2 warps per scheduler.  Here the row-block values are operands of the DFMA itself (uniform
-// register loaded by LDCU from the constant bank: no LSU/shared-memory traffic, no vector registers), the material is
-// a compile-time constant of an unrolled three-way branch (lanes of a warp whose chunks sit in different materials
-// take their branches one after the other), which halves the shared-memory wavefronts and brings the kernel under
-// 128 registers.  Template parameters select the variants measured on the B200 (tools/bench_imp_spmv.py):
-//   NSTAGE  1: one brick per block, more resident blocks hide the TMA latency; 2: two-stage mbarrier pipeline;
-//   MINB    resident blocks per SM the register allocation is bounded for;
-//   RU      unroll factor of the loop over the 9 neighbour rows.
-// Arithmetic (FMA order per accumulator) is that of k_spmv_dot / k_spmv_dot_tma: Ap is bit-identical.
+// k_spmv_dot_tmac: the TMA-tiled implicit SpMV, second generation (default).  Differences to k_spmv_dot_tma, each
+// taken from the ncu captures under profiles/r01c_* / r01d_*:
+//  * the three pure-material row blocks are passed BY VALUE as a __grid_constant__ kernel parameter (6.5 KB in the
+//    constant bank): the row-block value is an operand of the DFMA itself (uniform register filled by LDCU: no
+//    LSU/shared-memory traffic, no vector registers).  The material is a compile-time constant of a three-way branch
+//    (lanes of a warp whose chunks sit in different materials take their branches one after the other).  Halves the
+//    shared-memory wavefronts, 128..168 registers instead of 221;
+//  * TN = 7 or 8 nodes per thread and explicit tile descriptors with two lane shapes (8y x 4z and 4y x 8z rows per
+//    warp, both with a 60-row brick): at 30^3 (28 interior nodes per edge) the 8-node / 8x4 tiling of k_spmv_dot_tma
+//    executes 28672 node slots for 21952 nodes (77 %); 4 chunks of 7 nodes and a 4y x 8z strip for the last four
+//    y rows execute 22400 (98 %);
+//  * NSTAGE 1 (more resident blocks hide the TMA latency) or 2 (mbarrier pipeline), MINB resident blocks per SM, RU
+//    unroll of the loop over the 9 neighbour rows: variants measured by tools/bench_imp_spmv.py;
+//  * p.Ap of a thread is accumulated per component (3 independent chains instead of one of 72 additions).
+// Arithmetic of Ap (FMA order per accumulator) is that of k_spmv_dot / k_spmv_dot_tma: Ap is bit-identical.
 // ------------------------------------------------------------------------------------------------
 struct PureRows {
   double a[3 * RB_LEN];
 };
 
-template <int MAT, int RU, int PITCH>
+// x pitch of the p brick: even (rows stay 16-B aligned) with an odd number of 16-B units, so that the 128-bit loads
+// of the 8 y-rows of a quarter-warp fall into 8 different bank groups
+__host__ __device__ constexpr int tmac_pitch(int tn, int cb) {
+  int p = (tn * cb + 2 + (tn & 1) + 1) & ~1;  // odd tn: the brick may start one node early (16-B aligned TMA origin)
+  if (((p / 2) & 1) == 0) p += 2;
+  return p;
+}
+
+struct TileInfo2 {
+  int cb, tn, nchunk, pitch, ntiles;
+  const int4 *tiles;      // [ntiles] x: first chunk, y / z: interior coordinates of the tile origin, w: lane shape
+  const int *chunk_pure;  // [niz][niy][nchunk]: pure id | (TN-bit mask of the nodes to fix up) << 8
+  const int *fix_ptr;     // [ntiles + 1]
+  const int2 *fix;        // x: lx | ry << 8 | rz << 12 (position inside the tile), y: row-block id
+};
+
+// S: the thread's window [TN*w, TN*w + TN + 2) starts S doubles after the 16-B aligned address the loads start from
+template <int MAT, int RU, int PITCH, int TN, int S>
 __device__ __forceinline__ void tile_rows_apply_const(const PureRows &R, const double *__restrict__ brick, int bx0,
-                                                      int ry, int rz, double (&acc)[8][3]) {
+                                                      int ry, int rz, int by_rows, double (&acc)[8][3]) {
 #pragma unroll RU
   for (int row = 0; row < 9; ++row) {
     const int dk = row / 3, dj = row - dk * 3;  // 0..2 (offset + 1)
-    const int rbase = ((rz + dk) * (TILE_Y + 2) + (ry + dj)) * PITCH + bx0;
+    const int rbase = ((rz + dk) * by_rows + (ry + dj)) * PITCH + bx0;
     double pv[3][10];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -1418,8 +1438,8 @@ __device__ __forceinline__ void tile_rows_apply_const(const PureRows &R, const d
 #pragma unroll
       for (int fj = 0; fj < 3; ++fj) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const double pval = pv[fj][t + di];
+        for (int t = 0; t < TN; ++t) {
+          const double pval = pv[fj][t + di + S];
           acc[t][0] += a[fj] * pval;
           acc[t][1] += a[3 + fj] * pval;
           acc[t][2] += a[6 + fj] * pval;
@@ -1429,13 +1449,43 @@ __device__ __forceinline__ void tile_rows_apply_const(const PureRows &R, const d
   }
 }
 
-template <int CB, int NSTAGE, int MINB, int RU>
+// ODD: n0 is odd, i.e. the pairs (t, t + 1) with odd t are the 16-B aligned ones
+template <int TN, int ODD>
+__device__ __forceinline__ void store_ap_pairs(double *__restrict__ Ap, size_t npad, int n0, int keep,
+                                               const double (&acc)[8][3]) {
+#pragma unroll
+  for (int t = 0; t < TN; ++t) {
+    const bool pair_start = ((t + ODD) & 1) == 0 && t + 1 < TN;
+    const bool pair_second = ((t + ODD) & 1) == 1 && t >= 1;
+    if (pair_start) {
+      const int both = (keep >> t) & 3;
+      if (both == 3) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          *reinterpret_cast<double2 *>(Ap + d * npad + n0 + t) = make_double2(acc[t][d], acc[t + 1][d]);
+      } else if (both & 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Ap[d * npad + n0 + t] = acc[t][d];
+      } else if (both & 2) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Ap[d * npad + n0 + t + 1] = acc[t + 1][d];
+      }
+    } else if (!pair_second) {  // a single node at either end
+      if ((keep >> t) & 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Ap[d * npad + n0 + t] = acc[t][d];
+      }
+    }
+  }
+}
+
+template <int CB, int TN, int NSTAGE, int MINB, int RU>
 __global__ void __launch_bounds__(32 * CB, MINB)
-    k_spmv_dot_tmac(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V, TileInfo ti,
-                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PureRows R, int ntl, int rs,
-                    int force) {
+    k_spmv_dot_tmac(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V, TileInfo2 ti,
+                    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ PureRows R, int ntl, int rs, int force) {
   extern __shared__ unsigned char s_raw[];
-  constexpr int pitch = 8 * CB + 2;
+  constexpr int pitch = tmac_pitch(TN, CB);
   constexpr int BRICK = 3 * BRICK_ROWS * pitch;  // doubles
   constexpr int STAGE_BYTES = (BRICK * 8 + 127) / 128 * 128;
   __shared__ uint64_t s_full[NSTAGE];
@@ -1443,9 +1493,8 @@ __global__ void __launch_bounds__(32 * CB, MINB)
   __shared__ int s_done[NSTAGE];
   unsigned char *s_base = s_raw + ((128u - ((unsigned)__cvta_generic_to_shared(s_raw) & 127u)) & 127u);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
   const int tile0 = blockIdx.x * ntl;
-  const int nitems = min(ntl, ntiles - tile0) * rs;
+  const int nitems = min(ntl, ti.ntiles - tile0) * rs;
 
   if ((int)threadIdx.x < rs) {
     const int yy = (int)blockIdx.y * rs + (int)threadIdx.x + L.yoff;
@@ -1470,16 +1519,17 @@ __global__ void __launch_bounds__(32 * CB, MINB)
     return i;
   };
   auto issue = [&](int item, int stage) {  // one thread
-    const int tile = tile0 + item / rs, slot = s_slot[item % rs];
-    const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
+    const int4 td = __ldg(&ti.tiles[tile0 + item / rs]);
+    const int slot = s_slot[item % rs];
     mbar_expect_tx(&s_full[stage], BRICK * 8);
-    tma_load_5d(s_base + stage * STAGE_BYTES, &tmap, &s_full[stage], tx * 8 * CB, ty * TILE_Y, tz * TILE_Z, 0, slot);
+    // the box starts at an even x (16-B aligned global address): with TN = 7 odd tile origins start one node early
+    tma_load_5d(s_base + stage * STAGE_BYTES, td.w ? &tmap_b : &tmap_a, &s_full[stage], (td.x * TN) & ~1, td.y, td.z, 0,
+                slot);
   };
 
-  const int ry = lane & 7, rz = lane >> 3;
   const size_t npad = P.nn_pad;
   int cur = next_active(0), k = 0;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !(force & 4)) {
     int it = cur;
 #pragma unroll
     for (int q = 0; q < NSTAGE; ++q) {
@@ -1487,7 +1537,10 @@ __global__ void __launch_bounds__(32 * CB, MINB)
       it = it < nitems ? next_active(it + 1) : nitems;
     }
   }
-  int cur_tile = -1, pure = 0, keep = 0, n0 = 0, f0 = 0, f1 = 0, nfix0 = 0;
+  // per-tile thread state (independent of the slot: with ntl == 1 it is computed once per block)
+  int cur_tile = -1, pure = 0, keep = 0, n0 = 0, f0 = 0, f1 = 0, nfix0 = 0, ry = 0, rz = 0, by_rows = TILE_Y + 2;
+  int xoff = 0;  // 1: the brick starts one node before the tile (see issue())
+  const bool dbg_skip_compute = force & 2, dbg_skip_load = force & 4;  // measurement only (tools/bench_imp_spmv.py)
   bool work = false;
   while (cur < nitems) {
     const int nxt = next_active(cur + 1);
@@ -1495,48 +1548,70 @@ __global__ void __launch_bounds__(32 * CB, MINB)
     const int tile = tile0 + cur / rs, slot = s_slot[cur % rs];
     if (tile != cur_tile) {
       cur_tile = tile;
-      const int tx = tile % ti.tiles_x, tyz = tile / ti.tiles_x, ty = tyz % ti.tiles_y, tz = tyz / ti.tiles_y;
-      const int c = tx * CB + w, jj = ty * TILE_Y + ry, kk = tz * TILE_Z + rz;
+      const int4 td = __ldg(&ti.tiles[tile]);
+      // lane shape 0: 8 y-rows x 4 z-rows per warp (brick 10 x 6 rows); 1: 4 y-rows x 8 z-rows (brick 6 x 10 rows)
+      ry = td.w ? (lane & 3) : (lane & 7);
+      rz = td.w ? (lane >> 2) : (lane >> 3);
+      by_rows = td.w ? TILE_Z + 2 : TILE_Y + 2;
+      const int c = td.x + w, jj = td.y + ry, kk = td.z + rz;
       work = c < ti.nchunk && jj < P.niy && kk < P.niz;
       const int info = work ? __ldg(&ti.chunk_pure[(kk * P.niy + jj) * ti.nchunk + c]) : 0;
       pure = info & 0xff;
-      const int ii0 = c * 8;
-      const int nvalid = min(8, P.nix - ii0);
+      const int ii0 = c * TN;
+      const int nvalid = min(TN, P.nix - ii0);
       keep = work ? (((1 << nvalid) - 1) & ~(info >> 8)) : 0;  // nodes this thread stores itself
       n0 = (kk + 1) * P.nxny + (jj + 1) * P.nx + ii0 + 1;
       f0 = __ldg(&ti.fix_ptr[tile]);
       f1 = __ldg(&ti.fix_ptr[tile + 1]);
-      nfix0 = (ty * TILE_Y + 1) * P.nx + (tz * TILE_Z + 1) * P.nxny + tx * 8 * CB + 1;  // node of tile position 0
+      nfix0 = (td.y + 1) * P.nx + (td.z + 1) * P.nxny + td.x * TN + 1;  // node of tile position 0
+      xoff = (td.x * TN) & 1;
     }
     const double *s_brick = reinterpret_cast<const double *>(s_base + stage * STAGE_BYTES);
-    mbar_wait(&s_full[stage], (k / NSTAGE) & 1);
+    if (!dbg_skip_load) mbar_wait(&s_full[stage], (k / NSTAGE) & 1);
 
-    double red = 0.0;
+    double red0 = 0.0, red1 = 0.0, red2 = 0.0;
     double *Ap = V.Ap + (size_t)slot * V.vstride;
-    if (work) {
+    if (work && !dbg_skip_compute) {
       double acc[8][3];
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
-      if (pure == 0)
-        tile_rows_apply_const<0, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
-      else if (pure == 1)
-        tile_rows_apply_const<1, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
-      else
-        tile_rows_apply_const<2, RU, pitch>(R, s_brick, 8 * w, ry, rz, acc);
-      const int cbase = ((rz + 1) * (TILE_Y + 2) + (ry + 1)) * pitch + 8 * w + 1;
+      const int xs = TN * w + xoff, bx0 = xs & ~1;
+      if ((TN & 1) && (xs & 1)) {  // odd window start: loads begin one double earlier (warp-uniform)
+        if (pure == 0)
+          tile_rows_apply_const<0, RU, pitch, TN, TN & 1>(R, s_brick, bx0, ry, rz, by_rows, acc);
+        else if (pure == 1)
+          tile_rows_apply_const<1, RU, pitch, TN, TN & 1>(R, s_brick, bx0, ry, rz, by_rows, acc);
+        else
+          tile_rows_apply_const<2, RU, pitch, TN, TN & 1>(R, s_brick, bx0, ry, rz, by_rows, acc);
+      } else {
+        if (pure == 0)
+          tile_rows_apply_const<0, RU, pitch, TN, 0>(R, s_brick, bx0, ry, rz, by_rows, acc);
+        else if (pure == 1)
+          tile_rows_apply_const<1, RU, pitch, TN, 0>(R, s_brick, bx0, ry, rz, by_rows, acc);
+        else
+          tile_rows_apply_const<2, RU, pitch, TN, 0>(R, s_brick, bx0, ry, rz, by_rows, acc);
+      }
+      const int cbase = ((rz + 1) * by_rows + (ry + 1)) * pitch + xs + 1;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < TN; ++t) {
         if ((keep >> t) & 1) {
-          Ap[n0 + t] = acc[t][0];
-          Ap[npad + n0 + t] = acc[t][1];
-          Ap[2 * npad + n0 + t] = acc[t][2];
-          red += s_brick[cbase + t] * acc[t][0] + s_brick[BRICK_ROWS * pitch + cbase + t] * acc[t][1] +
-                 s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
+          red0 += s_brick[cbase + t] * acc[t][0];
+          red1 += s_brick[BRICK_ROWS * pitch + cbase + t] * acc[t][1];
+          red2 += s_brick[2 * BRICK_ROWS * pitch + cbase + t] * acc[t][2];
         }
       }
+      // Ap stores.  Lanes of a warp write different grid rows, so every store instruction costs one sector per lane
+      // whatever its width (ncu r01d: the L1 data pipe, not the FP64 pipe, limits k_spmv_dot_tma): nodes are paired
+      // into 16-B stores wherever both nodes are kept and the pair is 16-B aligned (node index even)
+      if (n0 & 1) {
+        store_ap_pairs<TN, 1>(Ap, npad, n0, keep, acc);
+      } else {
+        store_ap_pairs<TN, 0>(Ap, npad, n0, keep, acc);
+      }
     }
-    // fix-up: the nodes of this tile that sit on a material interface, one per thread (as in k_spmv_dot_tma)
-    for (int f = f0 + w * 32 + lane; f < f1; f += 32 * CB) {
+    // fix-up: the nodes of this tile that sit on a material interface, one per thread, shared evenly by the warps
+    // (the brick holds all the p values they need; their row blocks come from the L1/L2-resident table)
+    for (int f = f0 + w * 32 + lane; f < (dbg_skip_compute ? f0 : f1); f += 32 * CB) {
       const int2 e = __ldg(&ti.fix[f]);
       const int lx = e.x & 0xff, fy = (e.x >> 8) & 0xf, fz = (e.x >> 12) & 0xf;
       const double2 *a2 = reinterpret_cast<const double2 *>(V.rows + (size_t)e.y * RB_LEN);
@@ -1544,7 +1619,7 @@ __global__ void __launch_bounds__(32 * CB, MINB)
 #pragma unroll 3
       for (int row = 0; row < 9; ++row) {
         const int dk = row / 3, dj = row - dk * 3;
-        const int rb = ((fz + dk) * (TILE_Y + 2) + (fy + dj)) * pitch + lx;
+        const int rb = ((fz + dk) * by_rows + (fy + dj)) * pitch + lx + xoff;
 #pragma unroll
         for (int di = 0; di < 3; ++di) {
           double av[10];
@@ -1568,11 +1643,13 @@ __global__ void __launch_bounds__(32 * CB, MINB)
         }
       }
       const int n = nfix0 + fz * P.nxny + fy * P.nx + lx;
-      const int cb0 = ((fz + 1) * (TILE_Y + 2) + (fy + 1)) * pitch + lx + 1;
+      const int cb0 = ((fz + 1) * by_rows + (fy + 1)) * pitch + lx + xoff + 1;
       Ap[n] = y0;
       Ap[npad + n] = y1;
       Ap[2 * npad + n] = y2;
-      red += s_brick[cb0] * y0 + s_brick[BRICK_ROWS * pitch + cb0] * y1 + s_brick[2 * BRICK_ROWS * pitch + cb0] * y2;
+      red0 += s_brick[cb0] * y0;
+      red1 += s_brick[BRICK_ROWS * pitch + cb0] * y1;
+      red2 += s_brick[2 * BRICK_ROWS * pitch + cb0] * y2;
     }
     __syncwarp();
 
@@ -1584,13 +1661,15 @@ __global__ void __launch_bounds__(32 * CB, MINB)
         int after = nxt;
 #pragma unroll
         for (int q = 1; q < NSTAGE; ++q) after = after < nitems ? next_active(after + 1) : nitems;
-        if (after < nitems) {
+        if (after < nitems && !dbg_skip_load) {
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           issue(after, stage);
         }
       }
     }
-    red = warp_sum(red);
+    // p.Ap of this slot: one partial per (tile, warp) in plane FOLD_PLANE of the slot's partial-sum buffer, folded in
+    // a fixed order by k_fold_spmv (one warp per slot), which the kernel boundary orders after these stores
+    const double red = warp_sum((red0 + red1) + red2);
     if (lane == 0) T.partial[((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max + tile * CB + w] = red;
     cur = nxt;
     ++k;
@@ -1606,7 +1685,9 @@ __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, i
 }
 
 // cg_update / cg_pupdate of the implicit operator: k = 1/diag comes from the row table and z = k r is recomputed
-// instead of being stored (the same multiplication => the same bits); 144 + 72 B/node instead of 192 + 72.
+// instead of being stored (the same multiplication => the same bits).  x += alpha p (src/ell.cpp:102) is deferred to
+// the p update of the same iteration (or k_cg_finish after the last one), where p is read anyway:
+// 72 + 120 B/node per iteration instead of 144 + 72.
 __global__ void __launch_bounds__(NT)
     k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int nfold) {
   __shared__ double sm[NRED * (NT / 32)];
@@ -1619,14 +1700,12 @@ __global__ void __launch_bounds__(NT)
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   // the vector loads go out first: the fold below (and its barrier) then overlaps their latency
-  double pp[3], rr[3], ap[3], dd[3];
+  double rr[3], ap[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const size_t ix = vo + (size_t)d * P.nn_pad + (n < P.nn ? n : 0);
-    pp[d] = V.p[ix];
     rr[d] = V.r[ix];
     ap[d] = V.Ap[ix];
-    dd[d] = V.du[ix];
   }
   double alpha;
   if (nfold > 0) {
@@ -1652,7 +1731,6 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      V.du[ix] = dd[d] + alpha * pp[d];
       const double r = rr[d] - alpha * ap[d];
       V.r[ix] = r;
       const double z = __dmul_rn(imp_kk(P, V, n, d), r);  // rounded product, as when z is stored (k_cg_update)
@@ -1677,7 +1755,7 @@ __global__ void __launch_bounds__(NT)
   if (slot < 0) return;
   const mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
-  const double beta = st->beta;
+  const double beta = st->beta, alpha = st->alpha;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   if (n >= P.nn) return;
@@ -1685,7 +1763,9 @@ __global__ void __launch_bounds__(NT)
   for (int d = 0; d < 3; ++d) {
     const size_t ix = vo + (size_t)d * P.nn_pad + n;
     const double z = __dmul_rn(imp_kk(P, V, n, d), V.r[ix]);  // never fused into the FMA below
-    V.p[ix] = z + beta * V.p[ix];
+    const double pp = V.p[ix];
+    V.du[ix] = fma(alpha, pp, V.du[ix]);  // x += alpha p of this iteration (src/ell.cpp:102)
+    V.p[ix] = z + beta * pp;
   }
 }
 
@@ -1730,8 +1810,10 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
-// x += alpha p ; r -= alpha Ap ; z = k r ; z.z ; r.z   (src/ell.cpp:102-110), then the scalar tail
-// of the iteration and the loop-head test of the next one (src/ell.cpp:93-94,108-119).
+// r -= alpha Ap ; z = k r ; z.z ; r.z   (src/ell.cpp:103-110), then the scalar tail of the iteration and the
+// loop-head test of the next one (src/ell.cpp:93-94,108-119).  x += alpha p (src/ell.cpp:102) does not feed any
+// of these: it is applied by k_cg_pupdate of the same iteration, which reads p anyway, or -- after the last
+// iteration of a slot, whose p update is skipped -- by k_cg_finish.  Same FMA, same bits, 24 B/node less traffic.
 __global__ void __launch_bounds__(NT)
     k_cg_update(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
   __shared__ double sm[NRED * (NT / 32)];
@@ -1748,8 +1830,6 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double pp = V.p[ix];
-      V.du[ix] += alpha * pp;
       const double r = V.r[ix] - alpha * V.Ap[ix];
       V.r[ix] = r;
       const double z = V.k[ix] * r;
@@ -1776,14 +1856,35 @@ __global__ void __launch_bounds__(NT)
   if (slot < 0) return;
   const mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
-  const double beta = st->beta;
+  const double beta = st->beta, alpha = st->alpha;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
   if (n >= P.nn) return;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const size_t ix = vo + (size_t)d * P.nn_pad + n;
-    V.p[ix] = V.z[ix] + beta * V.p[ix];
+    const double pp = V.p[ix];
+    V.du[ix] = fma(alpha, pp, V.du[ix]);  // x += alpha p of this iteration (src/ell.cpp:102)
+    V.p[ix] = V.z[ix] + beta * pp;
+  }
+}
+
+// x += alpha p of the LAST iteration of every slot of the list that iterated at all: its p update was skipped because
+// the slot had left the loop (cg_active == 0), so the deferred update of du is still pending.  Runs once per solve.
+__global__ void __launch_bounds__(NT)
+    k_cg_finish(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  const mgpu_slot_state *st = &T.state[slot];
+  if (st->cg_its <= 0 || st->cg_active) return;
+  const double alpha = st->alpha;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= P.nn) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const size_t ix = vo + (size_t)d * P.nn_pad + n;
+    V.du[ix] = fma(alpha, V.p[ix], V.du[ix]);
   }
 }
 
@@ -2049,6 +2150,12 @@ struct mgpu_ctx {
   int tma_smem = 0;
   PureRows pure_rows;     // host copy of row blocks 0..2 (kernel parameter of k_spmv_dot_tmac)
   int tma_variant = 0;    // 0: k_spmv_dot_tma (row blocks in shared memory); v >= 1: k_spmv_dot_tmac variant v
+  TileInfo2 tile2;        // tiling of k_spmv_dot_tmac (7 or 8 nodes per thread, two lane shapes)
+  CUtensorMap tmap_a, tmap_b;  // V.p with the boxes of lane shape 0 (pitch x 10 x 6) and 1 (pitch x 6 x 10)
+  int tile2_smem = 0;     // bytes of one brick
+  int4 *d_tiles2 = nullptr;
+  int *d_chunk_pure2 = nullptr, *d_fix_ptr2 = nullptr;
+  int2 *d_fix2 = nullptr;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
   double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
@@ -2128,33 +2235,35 @@ inline tma_kernel_t tma_kernel(int cb) {
   }
 }
 
-// variants of k_spmv_dot_tmac (row blocks as a kernel parameter): {stages, resident blocks per SM, row unroll}
+// variants of k_spmv_dot_tmac: {stages, resident blocks per SM, row unroll}; variant ids are 1-based
 struct TmacVariant {
   int nstage, minb, ru;
 };
-constexpr int N_TMAC = 7;
-static const TmacVariant kTmac[N_TMAC] = {{2, 2, 1}, {2, 2, 3}, {1, 4, 1}, {1, 3, 3}, {1, 3, 1}, {2, 2, 9}, {1, 3, 9}};
-typedef void (*tmac_kernel_t)(const MeshConst, const Lst, int, SlotTables, VecPool, TileInfo, const CUtensorMap,
-                              const PureRows, int, int, int);
-template <int NS, int MB, int RU>
+constexpr int N_TMAC = 4;
+static const TmacVariant kTmac[N_TMAC] = {{2, 2, 1}, {1, 3, 1}, {1, 4, 1}, {2, 2, 3}};
+constexpr int TMAC_DEFAULT = 3;
+typedef void (*tmac_kernel_t)(const MeshConst, const Lst, int, SlotTables, VecPool, TileInfo2, const CUtensorMap,
+                              const CUtensorMap, const PureRows, int, int, int);
+template <int TN, int NS, int MB, int RU>
 inline tmac_kernel_t tmac_pick(int cb) {
   switch (cb) {
-    case 1: return k_spmv_dot_tmac<1, NS, MB, RU>;
-    case 2: return k_spmv_dot_tmac<2, NS, MB, RU>;
-    case 3: return k_spmv_dot_tmac<3, NS, MB, RU>;
-    default: return k_spmv_dot_tmac<4, NS, MB, RU>;
+    case 1: return k_spmv_dot_tmac<1, TN, NS, MB, RU>;
+    case 2: return k_spmv_dot_tmac<2, TN, NS, MB, RU>;
+    case 3: return k_spmv_dot_tmac<3, TN, NS, MB, RU>;
+    default: return k_spmv_dot_tmac<4, TN, NS, MB, RU>;
   }
 }
-inline tmac_kernel_t tmac_kernel(int variant, int cb) {  // variant 1..N_TMAC
+template <int TN>
+inline tmac_kernel_t tmac_kernel_tn(int variant, int cb) {
   switch (variant) {
-    case 1: return tmac_pick<2, 2, 1>(cb);
-    case 2: return tmac_pick<2, 2, 3>(cb);
-    case 3: return tmac_pick<1, 4, 1>(cb);
-    case 4: return tmac_pick<1, 3, 3>(cb);
-    case 5: return tmac_pick<1, 3, 1>(cb);
-    case 6: return tmac_pick<2, 2, 9>(cb);
-    default: return tmac_pick<1, 3, 9>(cb);
+    case 1: return tmac_pick<TN, 2, 2, 1>(cb);
+    case 2: return tmac_pick<TN, 1, 3, 1>(cb);
+    case 3: return tmac_pick<TN, 1, 4, 1>(cb);
+    default: return tmac_pick<TN, 2, 2, 3>(cb);
   }
+}
+inline tmac_kernel_t tmac_kernel(int variant, int cb, int tn) {  // variant 1..N_TMAC
+  return tn == 7 ? tmac_kernel_tn<7>(variant, cb) : tmac_kernel_tn<8>(variant, cb);
 }
 
 struct ProfScope {
@@ -2589,12 +2698,99 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
           c->imp_kernel = 2;
           c->tma_smem = 2 * ((c->tile_smem + 127) / 128 * 128) + 128;
           CK(cudaFuncSetAttribute(tma_kernel(ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize, c->tma_smem));
-          if (ti.cb <= 4) {
-            for (int v = 1; v <= N_TMAC; ++v)
-              CK(cudaFuncSetAttribute(tmac_kernel(v, ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kTmac[v - 1].nstage * ((c->tile_smem + 127) / 128 * 128) + 128));
-            if (const char *env = getenv("MICROPP_TMA_VARIANT"))
-              c->tma_variant = std::min(std::max(atoi(env), 0), N_TMAC);
+          // ---- tiling of k_spmv_dot_tmac: TN nodes per thread, cb warps per block, tile descriptors ----
+          {
+            TileInfo2 &t2 = c->tile2;
+            long best = -1;
+            for (int tn = 8; tn >= 7; --tn)
+              for (int cb = 4; cb >= 1; --cb) {
+                const int nch = (P.nix + tn - 1) / tn;
+                if (cb > nch) continue;
+                const long exec = (long)((nch + cb - 1) / cb) * cb * tn;  // executed node slots per x row
+                // fewer executed slots; blocks of 1 or 2 warps pay for their relatively larger halo and overheads
+                const long score = exec * (cb >= 3 ? 100 : cb == 2 ? 115 : 140) + (4 - cb);
+                if (best < 0 || score < best) {
+                  best = score;
+                  t2.tn = tn;
+                  t2.cb = cb;
+                }
+              }
+            const int TN = t2.tn;
+            t2.nchunk = (P.nix + TN - 1) / TN;
+            t2.pitch = tmac_pitch(TN, t2.cb);
+            c->tile2_smem = (int)(sizeof(double) * 3 * BRICK_ROWS * t2.pitch);
+            // y is covered by 8-row tiles of lane shape 0; a remainder of 1..4 rows becomes a strip of shape-1 tiles
+            const int yrem = P.niy % TILE_Y, y_a = (yrem >= 1 && yrem <= 4) ? P.niy - yrem : P.niy;
+            std::vector<int4> tiles;
+            const int tiles_x = (t2.nchunk + t2.cb - 1) / t2.cb;
+            for (int z0 = 0; z0 < P.niz; z0 += TILE_Z)
+              for (int y0 = 0; y0 < y_a; y0 += TILE_Y)
+                for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y0, z0, 0));
+            if (y_a < P.niy)
+              for (int z0 = 0; z0 < P.niz; z0 += TILE_Y)
+                for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y_a, z0, 1));
+            t2.ntiles = (int)tiles.size();
+            std::vector<int> chunk_pure((size_t)P.niz * P.niy * t2.nchunk, 0), fix_ptr(t2.ntiles + 1, 0);
+            std::vector<int2> fix;
+            for (int tile = 0; tile < t2.ntiles; ++tile) {
+              const int4 td = tiles[tile];
+              fix_ptr[tile] = (int)fix.size();
+              const int ny_t = td.w ? TILE_Z : TILE_Y, nz_t = td.w ? TILE_Y : TILE_Z;
+              for (int rz = 0; rz < nz_t; ++rz)
+                for (int ry = 0; ry < ny_t; ++ry)
+                  for (int wq = 0; wq < t2.cb; ++wq) {
+                    const int kk = td.z + rz, jj = td.y + ry, cc = td.x + wq;
+                    if (kk >= P.niz || jj >= P.niy || cc >= t2.nchunk) continue;
+                    const int m0 = (kk * P.niy + jj) * P.nix + cc * TN, nv = std::min(TN, P.nix - cc * TN);
+                    int cnt[3] = {0, 0, 0};
+                    for (int t = 0; t < nv; ++t)
+                      if (rowid[m0 + t] < 3) cnt[rowid[m0 + t]]++;
+                    int pure = 0;
+                    for (int q = 1; q < 3; ++q)
+                      if (cnt[q] > cnt[pure]) pure = q;
+                    int mask = 0;
+                    for (int t = 0; t < nv; ++t)
+                      if (rowid[m0 + t] != pure) {
+                        mask |= 1 << t;
+                        int2 e;
+                        e.x = (wq * TN + t) | (ry << 8) | (rz << 12);
+                        e.y = rowid[m0 + t];
+                        fix.push_back(e);
+                      }
+                    chunk_pure[((size_t)kk * P.niy + jj) * t2.nchunk + cc] = pure | (mask << 8);
+                  }
+            }
+            fix_ptr[t2.ntiles] = (int)fix.size();
+            CK(cudaMalloc(&c->d_tiles2, sizeof(int4) * tiles.size()));
+            CK(cudaMemcpy(c->d_tiles2, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_chunk_pure2, sizeof(int) * chunk_pure.size()));
+            CK(cudaMemcpy(c->d_chunk_pure2, chunk_pure.data(), sizeof(int) * chunk_pure.size(), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_fix_ptr2, sizeof(int) * fix_ptr.size()));
+            CK(cudaMemcpy(c->d_fix_ptr2, fix_ptr.data(), sizeof(int) * fix_ptr.size(), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_fix2, sizeof(int2) * std::max<size_t>(fix.size(), 1)));
+            if (!fix.empty()) CK(cudaMemcpy(c->d_fix2, fix.data(), sizeof(int2) * fix.size(), cudaMemcpyHostToDevice));
+            t2.tiles = c->d_tiles2;
+            t2.chunk_pure = c->d_chunk_pure2;
+            t2.fix_ptr = c->d_fix_ptr2;
+            t2.fix = c->d_fix2;
+            const cuuint32_t box_a[5] = {(cuuint32_t)t2.pitch, TILE_Y + 2, TILE_Z + 2, 3, 1};
+            const cuuint32_t box_b[5] = {(cuuint32_t)t2.pitch, TILE_Z + 2, TILE_Y + 2, 3, 1};
+            const CUresult ra = ((encode_t)fn)(&c->tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void *)V.p, gdim, gstr,
+                                               box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            const CUresult rb = ((encode_t)fn)(&c->tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void *)V.p, gdim, gstr,
+                                               box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ra == CUDA_SUCCESS && rb == CUDA_SUCCESS && t2.ntiles * t2.cb <= nblk_max) {
+              for (int v = 1; v <= N_TMAC; ++v)
+                CK(cudaFuncSetAttribute(tmac_kernel(v, t2.cb, TN), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kTmac[v - 1].nstage * ((c->tile2_smem + 127) / 128 * 128) + 128));
+              c->tma_variant = TMAC_DEFAULT;
+              if (const char *env = getenv("MICROPP_TMA_VARIANT"))
+                c->tma_variant = std::min(std::max(atoi(env), 0), N_TMAC);
+            } else {
+              t2.ntiles = 0;  // k_spmv_dot_tmac unavailable: k_spmv_dot_tma serves kernel 2
+            }
           }
         } else {
           fprintf(stderr, "micropp-b200: cuTensorMapEncodeTiled failed (%d); using the cp.async tiled kernel\n", (int)r);
@@ -2658,6 +2854,10 @@ void mgpu_destroy(mgpu_ctx *c) {
   if (c->d_chunk_id) cudaFree(c->d_chunk_id);
   if (c->d_chunk_pure) cudaFree(c->d_chunk_pure);
   if (c->d_fix_ptr) cudaFree(c->d_fix_ptr);
+  if (c->d_tiles2) cudaFree(c->d_tiles2);
+  if (c->d_chunk_pure2) cudaFree(c->d_chunk_pure2);
+  if (c->d_fix_ptr2) cudaFree(c->d_fix_ptr2);
+  if (c->d_fix2) cudaFree(c->d_fix2);
   if (c->d_fix) cudaFree(c->d_fix);
   cudaFree(c->T.state);
   cudaFree((void *)c->T.vars_old);
@@ -2893,22 +3093,39 @@ static void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
   const int ntiles = ti.tiles_x * ti.tiles_y * ti.tiles_z;
   // kern 2: the context's TMA kernel; kern 10 + v: TMA variant v (0 = k_spmv_dot_tma, v >= 1 = k_spmv_dot_tmac)
   int variant = c->tma_variant;
+  if (kern >= 100) {  // measurement only: 100 = skip the compute, 200 = skip the loads (k_spmv_dot_tmac)
+    force |= (kern / 100) << 1;
+    kern %= 100;
+  }
   if (kern >= 10) {
-    variant = std::min(kern - 10, ti.cb <= 4 ? N_TMAC : 0);
+    variant = std::min(kern - 10, N_TMAC);
     kern = 2;
   }
+  if (c->tile2.ntiles == 0) variant = 0;
   kern = imp_kernel_of(c, kern);
   if (kern == 2) {
-    const int rs = std::min(TMA_MAX_RS, n), ntl = rs >= 4 ? 1 : TMA_MAX_RS / rs;
-    const dim3 grid((ntiles + ntl - 1) / ntl, (n + rs - 1) / rs);
+    int rs = std::min(TMA_MAX_RS, n), ntl = rs >= 4 ? 1 : TMA_MAX_RS / rs;
     if (variant >= 1) {
-      const int smem = kTmac[variant - 1].nstage * ((c->tile_smem + 127) / 128 * 128) + 128;
-      tmac_kernel(variant, ti.cb)<<<grid, 32 * ti.cb, smem, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, ti,
-                                                                        c->tmap_p, c->pure_rows, ntl, rs, force);
-    } else {
-      tma_kernel(ti.cb)<<<grid, 32 * ti.cb, c->tma_smem, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, ti,
-                                                                     c->tmap_p, ntl, rs, force);
+      const TileInfo2 &t2 = c->tile2;
+      // small groups of slots (MICROPP_CG_GROUP): fewer slots per block so that the grid still fills 148 SMs
+      const long want_blocks = 148L * 4 * 2;
+      rs = (int)std::max(1L, std::min((long)rs, (long)n * t2.ntiles / want_blocks));
+      ntl = 1;
+      if (n < 4) {
+        rs = n;
+        ntl = TMA_MAX_RS / rs;
+      }
+      const dim3 grid((t2.ntiles + ntl - 1) / ntl, (n + rs - 1) / rs);
+      const int smem = kTmac[variant - 1].nstage * ((c->tile2_smem + 127) / 128 * 128) + 128;
+      tmac_kernel(variant, t2.cb, t2.tn)<<<grid, 32 * t2.cb, smem, c->stream>>>(
+          c->mc, lst_of(c, l), n, c->T, c->V, t2, c->tmap_a, c->tmap_b, c->pure_rows, ntl, rs, force);
+      k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, t2.ntiles * t2.cb, force);
+      c->launches++;
+      return;
     }
+    const dim3 grid((ntiles + ntl - 1) / ntl, (n + rs - 1) / rs);
+    tma_kernel(ti.cb)<<<grid, 32 * ti.cb, c->tma_smem, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, ti, c->tmap_p,
+                                                                   ntl, rs, force);
     // p.Ap: one warp per slot folds the per-(tile, warp) partials in a fixed order and runs the scalar tail
     k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, ntiles * ti.cb, force);
     c->launches++;
@@ -2920,8 +3137,12 @@ static void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
   }
 }
 
-// -1: no implicit operator; else the SpMV kernel it runs (0 simple, 1 tiled cp.async, 2 tiled TMA)
-int mgpu_implicit_kernel(const mgpu_ctx *c) { return c->implicit ? imp_kernel_of(c, c->imp_kernel) : -1; }
+// -1: no implicit operator; else the SpMV kernel it runs (0 simple, 1 tiled cp.async, 2 k_spmv_dot_tma, 3 k_spmv_dot_tmac)
+int mgpu_implicit_kernel(const mgpu_ctx *c) {
+  if (!c->implicit) return -1;
+  const int k = imp_kernel_of(c, c->imp_kernel);
+  return (k == 2 && c->tma_variant >= 1 && c->tile2.ntiles > 0) ? 3 : k;  // 3: k_spmv_dot_tmac
+}
 
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
@@ -2960,6 +3181,12 @@ void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
     k_cg_pupdate_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   else
     k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  CK(cudaGetLastError());
+}
+void mgpu_cg_finish(mgpu_ctx *c, int l, int n) {
+  if (n <= 0) return;
+  ProfScope ps(c, 3, n);
+  k_cg_finish<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
@@ -3004,12 +3231,16 @@ void mgpu_clear_nl_flags(mgpu_ctx *c, int l, int n) {
   CK(cudaGetLastError());
 }
 int mgpu_compact(mgpu_ctx *c, int list_in, int n_in, int list_out, int mode) {
+  return mgpu_compact_range(c, list_in, 0, n_in, list_out, mode);
+}
+// same over entries [off, off + n_in) of list_in (a group of the wave)
+int mgpu_compact_range(mgpu_ctx *c, int list_in, int off, int n_in, int list_out, int mode) {
   if (n_in <= 0) return 0;
   c->launches++;
   // lists 1 (Newton) and 2 (CG) keep their length on the device too: the step graphs start from it
   int *count2 = list_out == 1 ? c->d_cnt2 : (list_out == 2 ? c->d_cnt2 + 1 : nullptr);
-  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in], n_in, nullptr, c->d_list[list_out], c->d_count, count2, c->T,
-                                       mode, cudaGraphConditionalHandle(), 0, nullptr);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in] + off, n_in, nullptr, c->d_list[list_out], c->d_count, count2,
+                                       c->T, mode, cudaGraphConditionalHandle(), 0, nullptr);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(c->h_count, c->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -3085,6 +3316,7 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
   const unsigned long long l2 = c->launches;
   capture_begin(c, g, &wnode, 1);
   c->dyn_count = c->d_cnt2;
+  mgpu_cg_finish(c, 1, B);
   mgpu_axpy_u(c, 1, B);
   mgpu_asm_rhs(c, 1, B, 1);
   k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[1], c->d_cnt2, nullptr, c->T, 0, cond, 0,

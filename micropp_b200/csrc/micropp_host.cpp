@@ -202,6 +202,7 @@ micropp<3>::micropp(const micropp_params_t &params)
   engine->use_A0 = use_A0;
   engine->its_with_A0 = its_with_A0;
   if (const char *env = getenv("MICROPP_CG_CHUNK")) engine->cg_chunk = std::max(1, atoi(env));
+  if (const char *env = getenv("MICROPP_CG_GROUP")) engine->cg_group = std::max(0, atoi(env));
   if (const char *env = getenv("MICROPP_GRAPHS")) engine->use_graphs = atoi(env) != 0;
 
   if (use_A0) {

@@ -82,6 +82,7 @@ def _bind(lib):
         "mgpu_cg_init": (None, [V, C.c_int, C.c_int, C.c_int]),
         "mgpu_cg_spmv_dot": (None, [V, C.c_int, C.c_int, C.c_int]),
         "mgpu_cg_update": (None, [V, C.c_int, C.c_int]), "mgpu_cg_pupdate": (None, [V, C.c_int, C.c_int]),
+        "mgpu_cg_finish": (None, [V, C.c_int, C.c_int]),
         "mgpu_axpy_u": (None, [V, C.c_int, C.c_int]), "mgpu_ave_stress": (None, [V, C.c_int, C.c_int]),
         "mgpu_tail": (None, [V, C.c_int, C.c_int, C.c_int, C.c_int]),
         "mgpu_fetch_state": (None, [V, C.c_int, _ip, C.POINTER(SlotState)]),
@@ -240,6 +241,7 @@ class SlabRVE:
                 self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, self.op), 1, 2)
                 self._reduced(lib.mgpu_cg_update, (L0, 1), 2, 3)
                 self._each(lib.mgpu_cg_pupdate, L0, 1)
+        self._each(lib.mgpu_cg_finish, L0, 1)   # the deferred x += alpha p of the last iteration
 
     def homogenize(self, eps) -> dict:
         """set_displ_bc -> Newton-Raphson (src/solve.cpp:29-82) -> averaged stress (src/average.cpp:58-82)."""

@@ -115,7 +115,8 @@ def test_use_A0_on_elastic_rve_matches(mpp):
 
 
 @pytest.mark.parametrize("dims", [(14, 9, 8), (12, 12, 12), (30, 7, 6), (19, 12, 5), (3, 3, 3), (11, 10, 13),
-                                  (40, 11, 7), (66, 5, 6), (4, 4, 4)])
+                                  (40, 11, 7), (66, 5, 6), (4, 4, 4), (30, 30, 30), (16, 14, 21), (24, 12, 9),
+                                  (10, 6, 14), (50, 8, 8)])
 def test_operator_application_three_ways(mpp, refpy, dims):
     """A p through the assembled ELL matrix, the simple implicit kernel and the tiled implicit kernel: identical
     bits; and equal to the reference's ell_mvp on the reference's own assembled matrix."""
@@ -132,9 +133,10 @@ def test_operator_application_three_ways(mpp, refpy, dims):
     y0, d0 = g.apply_operator(p, op=0)
     y1, d1 = g.apply_operator(p, op=3, kernel=0)
     assert np.array_equal(y0, y1) and d0 == d1
-    # 1 = cp.async tiles, 2 = the context's TMA kernel, 10 + v = every TMA variant (0: row blocks in shared memory,
-    # 1..7: row blocks as a kernel parameter -- k_spmv_dot_tmac with 1/2 stages, 2/3/4 blocks per SM, row unroll 1/3/9)
-    for kernel in (1, 2) + tuple(range(10, 18)):
+    # 1 = cp.async tiles, 2 = the context's TMA kernel, 10 = k_spmv_dot_tma (row blocks in shared memory, 8 nodes per
+    # thread), 11..13 = the k_spmv_dot_tmac variants (row blocks as a kernel parameter, 7 or 8 nodes per thread, tile
+    # descriptors with two lane shapes; 2 stages / 1 stage x 3 blocks per SM / 1 stage x 4 blocks per SM)
+    for kernel in (1, 2, 10, 11, 12, 13, 14):
         y2, d2 = g.apply_operator(p, op=3, kernel=kernel)
         assert np.array_equal(y0, y2), kernel
         assert abs(d2 - d0) <= 1e-13 * abs(d0), kernel

@@ -31,12 +31,11 @@ p = rng.uniform(-1, 1, m.nndim)
 y0, d0 = m.apply_operator(p, op=3, kernel=0)
 flop = 2.0 * 243 * (n - 2) ** 3 * ngp
 peak = 148 * 64 * 2 * 1.965e9
-names = {0: "tma (rows in smem, 2 stages, 2 blocks/SM)", 1: "tmac 2 stages, 2 blocks/SM, unroll 1",
-         2: "tmac 2 stages, 2 blocks/SM, unroll 3", 3: "tmac 1 stage, 4 blocks/SM, unroll 1",
-         4: "tmac 1 stage, 3 blocks/SM, unroll 3", 5: "tmac 1 stage, 3 blocks/SM, unroll 1",
-         6: "tmac 2 stages, 2 blocks/SM, unroll 9", 7: "tmac 1 stage, 3 blocks/SM, unroll 9"}
+names = {0: "k_spmv_dot_tma (rows in smem, 8 nodes/thread, 2 stages, 2 blocks/SM)",
+         1: "k_spmv_dot_tmac 2 stages, 2 blocks/SM, unroll 1", 2: "k_spmv_dot_tmac 1 stage, 3 blocks/SM, unroll 1",
+         3: "k_spmv_dot_tmac 1 stage, 4 blocks/SM, unroll 1", 4: "k_spmv_dot_tmac 2 stages, 2 blocks/SM, unroll 3"}
 from bench import ClockSampler
-only = [int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4,5,6,7").split(",")]
+only = [int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4").split(",")]
 long_iters = int(os.environ.get("LONG_ITERS", "0"))   # > 0: one long run per variant with nvidia-smi clock sampling
 out = []
 for v in only:
@@ -50,6 +49,10 @@ for v in only:
         ms = m.bench_imp_spmv(ngp, long_iters, 10 + v)
         clk = cs.stop()
     tf = flop / (ms * 1e-3) / 1e12
+    if v >= 1 and os.environ.get("SPLIT"):
+        t_nocompute = min(m.bench_imp_spmv(ngp, iters, 110 + v) for _ in range(2))
+        t_noload = min(m.bench_imp_spmv(ngp, iters, 210 + v) for _ in range(2))
+        print(f"   variant {v}: loads + stores only {t_nocompute:.3f} ms; compute on a stale brick only {t_noload:.3f} ms", flush=True)
     out.append(dict(variant=v, name=names[v], ms=ms, tflops=tf, frac_fp64_peak=tf * 1e12 / peak, bit_identical=same, clocks=clk))
     print(f"variant {v}: {ms:8.3f} ms  {tf:6.2f} TFLOP/s  {tf*1e12/peak:5.1%} of FP64 peak  bits_ok={same}  {names[v]}  clocks={clk}", flush=True)
 print(json.dumps({"case": case, "fix_nodes": m.lib.micropp3x_implicit_rows(__import__("ctypes").byref(m.h)), "rve": n, "ngp": ngp, "iters": iters, "variants": out}))
