@@ -803,6 +803,7 @@ __global__ void __launch_bounds__(NT)
 // assembled path.
 // ------------------------------------------------------------------------------------------------
 constexpr int MR = 8;  // right-hand sides per thread
+constexpr int UPD_VPT = 2;  // nodes per thread of k_cg_update / k_cg_update_imp
 
 // blockIdx.y = group of R consecutive entries of the slot list (n_list entries; inside a graph the device-side count)
 template <int R>
@@ -1688,7 +1689,7 @@ __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, i
 // instead of being stored (the same multiplication => the same bits).  x += alpha p (src/ell.cpp:102) is deferred to
 // the p update of the same iteration (or k_cg_finish after the last one), where p is read anyway:
 // 72 + 120 B/node per iteration instead of 144 + 72.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
     k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int nfold) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
@@ -1698,14 +1699,27 @@ __global__ void __launch_bounds__(NT)
   mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
   const size_t vo = (size_t)slot * V.vstride;
-  const int n = blockIdx.x * NT + threadIdx.x;
-  // the vector loads go out first: the fold below (and its barrier) then overlaps their latency
-  double rr[3], ap[3];
+  // UPD_VPT nodes per thread (ncu r01h: one node per thread left the kernel latency-bound at 4.0 TB/s -- three
+  // dependent loads (row id -> 1/diag -> product) and one block reduction per 256 nodes): all vector loads and the
+  // row ids go out first, the fold below (and its barrier) then overlaps their latency
+  const int nb = blockIdx.x * (NT * UPD_VPT) + threadIdx.x;
+  double rr[UPD_VPT][3], ap[UPD_VPT][3];
+  int rid[UPD_VPT];  // row-block id of the node (-1: boundary node, k = 1)
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const size_t ix = vo + (size_t)d * P.nn_pad + (n < P.nn ? n : 0);
-    rr[d] = V.r[ix];
-    ap[d] = V.Ap[ix];
+  for (int v = 0; v < UPD_VPT; ++v) {
+    const int n = nb + v * NT;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t ix = vo + (size_t)d * P.nn_pad + (n < P.nn ? n : 0);
+      rr[v][d] = V.r[ix];
+      ap[v][d] = V.Ap[ix];
+    }
+    rid[v] = -1;
+    if (n < P.nn) {
+      int i, j, k;
+      node_ijk(P, n, i, j, k);
+      if (!on_boundary(P, i, j, k)) rid[v] = __ldg(&V.rowid[interior_index(P, i, j, k)]);
+    }
   }
   double alpha;
   if (nfold > 0) {
@@ -1727,15 +1741,20 @@ __global__ void __launch_bounds__(NT)
     alpha = st->alpha;
   }
   double red[2] = {0.0, 0.0};
-  if (n < P.nn) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double r = rr[d] - alpha * ap[d];
-      V.r[ix] = r;
-      const double z = __dmul_rn(imp_kk(P, V, n, d), r);  // rounded product, as when z is stored (k_cg_update)
-      red[0] += z * z;
-      red[1] += r * z;
+  for (int v = 0; v < UPD_VPT; ++v) {
+    const int n = nb + v * NT;
+    if (n < P.nn) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const size_t ix = vo + (size_t)d * P.nn_pad + n;
+        const double r = rr[v][d] - alpha * ap[v][d];
+        V.r[ix] = r;
+        const double kd = rid[v] < 0 ? 1.0 : __ldg(&V.rkinv[rid[v] * 3 + d]);  // as imp_kk: 1 / diagonal
+        const double z = __dmul_rn(kd, r);  // rounded product, as when z is stored (k_cg_update)
+        red[0] += z * z;
+        red[1] += r * z;
+      }
     }
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
@@ -1814,7 +1833,7 @@ __global__ void __launch_bounds__(NT)
 // loop-head test of the next one (src/ell.cpp:93-94,108-119).  x += alpha p (src/ell.cpp:102) does not feed any
 // of these: it is applied by k_cg_pupdate of the same iteration, which reads p anyway, or -- after the last
 // iteration of a slot, whose p update is skipped -- by k_cg_finish.  Same FMA, same bits, 24 B/node less traffic.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
     k_cg_update(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
   __shared__ double sm[NRED * (NT / 32)];
   __shared__ int sflag;
@@ -1824,18 +1843,35 @@ __global__ void __launch_bounds__(NT)
   if (!st->cg_active) return;
   const double alpha = st->alpha;
   const size_t vo = (size_t)slot * V.vstride;
-  const int n = blockIdx.x * NT + threadIdx.x;
-  double red[2] = {0.0, 0.0};
-  if (n < P.nn) {
+  // UPD_VPT nodes per thread, same node order and summation order as k_cg_update_imp (bit-identical sums)
+  const int nb = blockIdx.x * (NT * UPD_VPT) + threadIdx.x;
+  double rr[UPD_VPT][3], ap[UPD_VPT][3], kk[UPD_VPT][3];
+#pragma unroll
+  for (int v = 0; v < UPD_VPT; ++v) {
+    const int n = nb + v * NT;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const size_t ix = vo + (size_t)d * P.nn_pad + n;
-      const double r = V.r[ix] - alpha * V.Ap[ix];
-      V.r[ix] = r;
-      const double z = V.k[ix] * r;
-      V.z[ix] = z;
-      red[0] += z * z;
-      red[1] += r * z;
+      const size_t ix = vo + (size_t)d * P.nn_pad + (n < P.nn ? n : 0);
+      rr[v][d] = V.r[ix];
+      ap[v][d] = V.Ap[ix];
+      kk[v][d] = V.k[ix];
+    }
+  }
+  double red[2] = {0.0, 0.0};
+#pragma unroll
+  for (int v = 0; v < UPD_VPT; ++v) {
+    const int n = nb + v * NT;
+    if (n < P.nn) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const size_t ix = vo + (size_t)d * P.nn_pad + n;
+        const double r = rr[v][d] - alpha * ap[v][d];
+        V.r[ix] = r;
+        const double z = kk[v][d] * r;
+        V.z[ix] = z;
+        red[0] += z * z;
+        red[1] += r * z;
+      }
     }
   }
   double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
@@ -2204,6 +2240,7 @@ namespace {
 inline Lst lst_of(const mgpu_ctx *c, int l, int off = 0) { return Lst{c->d_list[l], c->dyn_count, off}; }
 inline dim3 int_grid(const mgpu_ctx *c, int n) { return dim3(std::max((c->mc.nint + NT - 1) / NT, 1), n, 1); }
 inline dim3 node_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT - 1) / NT, n, 1); }
+inline dim3 upd_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nn + NT * UPD_VPT - 1) / (NT * UPD_VPT), n, 1); }
 inline dim3 elem_grid(const mgpu_ctx *c, int n) { return dim3((c->mc.nelem + NT - 1) / NT, n, 1); }
 
 typedef void (*tile_kernel_t)(const MeshConst, const Lst, SlotTables, VecPool, TileInfo, int);
@@ -3169,9 +3206,9 @@ void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 3, n);
   if (c->cg_op == OP_IMPLICIT)
-    k_cg_update_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, imp_fold_count(c));
+    k_cg_update_imp<<<upd_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, imp_fold_count(c));
   else
-    k_cg_update<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+    k_cg_update<<<upd_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
   CK(cudaGetLastError());
 }
 void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
