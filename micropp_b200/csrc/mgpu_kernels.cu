@@ -1411,7 +1411,9 @@ struct TileInfo2 {
   const int4 *tiles;      // [ntiles] x: first chunk, y / z: interior coordinates of the tile origin, w: lane shape
   const int *chunk_pure;  // [niz][niy][nchunk]: pure id | (TN-bit mask of the nodes to fix up) << 8
   const int *fix_ptr;     // [ntiles + 1]
-  const int2 *fix;        // x: lx | ry << 8 | rz << 12 (position inside the tile), y: row-block id
+  // fix-up tasks: one or two interface nodes that share a row block.  x: position of node A inside the tile
+  // (lx | ry << 8 | rz << 12), y: position of node B or -1, z: row-block id
+  const int4 *fix;
 };
 
 // S: the thread's window [TN*w, TN*w + TN + 2) starts S doubles after the 16-B aligned address the loads start from
@@ -1610,17 +1612,23 @@ __global__ void __launch_bounds__(32 * CB, MINB)
         store_ap_pairs<TN, 0>(Ap, npad, n0, keep, acc);
       }
     }
-    // fix-up: the nodes of this tile that sit on a material interface, one per thread, shared evenly by the warps
-    // (the brick holds all the p values they need; their row blocks come from the L1/L2-resident table)
+    // fix-up: the nodes of this tile that sit on a material interface (the brick holds all the p values they need;
+    // their row blocks come from the L2-resident table).  One task per thread: ONE row block applied to one or two
+    // nodes (6 independent accumulator chains instead of 3, half the row-block loads); tasks are sorted by row
+    // block, so neighbouring lanes fetch the same sectors.
     for (int f = f0 + w * 32 + lane; f < (dbg_skip_compute ? f0 : f1); f += 32 * CB) {
-      const int2 e = __ldg(&ti.fix[f]);
-      const int lx = e.x & 0xff, fy = (e.x >> 8) & 0xf, fz = (e.x >> 12) & 0xf;
-      const double2 *a2 = reinterpret_cast<const double2 *>(V.rows + (size_t)e.y * RB_LEN);
-      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      const int4 e = __ldg(&ti.fix[f]);
+      const bool two = e.y >= 0;
+      const int eb = two ? e.y : e.x;
+      const int lxa = e.x & 0xff, fya = (e.x >> 8) & 0xf, fza = (e.x >> 12) & 0xf;
+      const int lxb = eb & 0xff, fyb = (eb >> 8) & 0xf, fzb = (eb >> 12) & 0xf;
+      const double2 *a2 = reinterpret_cast<const double2 *>(V.rows + (size_t)e.z * RB_LEN);
+      double ya0 = 0.0, ya1 = 0.0, ya2 = 0.0, yb0 = 0.0, yb1 = 0.0, yb2 = 0.0;
 #pragma unroll 3
       for (int row = 0; row < 9; ++row) {
         const int dk = row / 3, dj = row - dk * 3;
-        const int rb = ((fz + dk) * by_rows + (fy + dj)) * pitch + lx + xoff;
+        const int ra = ((fza + dk) * by_rows + (fya + dj)) * pitch + lxa + xoff;
+        const int rb = ((fzb + dk) * by_rows + (fyb + dj)) * pitch + lxb + xoff;
 #pragma unroll
         for (int di = 0; di < 3; ++di) {
           double av[10];
@@ -1630,27 +1638,50 @@ __global__ void __launch_bounds__(32 * CB, MINB)
             av[2 * q] = v.x;
             av[2 * q + 1] = v.y;
           }
-          const double px = s_brick[rb + di], py = s_brick[BRICK_ROWS * pitch + rb + di],
-                       pz = s_brick[2 * BRICK_ROWS * pitch + rb + di];
-          y0 += av[0] * px;
-          y0 += av[1] * py;
-          y0 += av[2] * pz;
-          y1 += av[3] * px;
-          y1 += av[4] * py;
-          y1 += av[5] * pz;
-          y2 += av[6] * px;
-          y2 += av[7] * py;
-          y2 += av[8] * pz;
+          const double pxa = s_brick[ra + di], pya = s_brick[BRICK_ROWS * pitch + ra + di],
+                       pza = s_brick[2 * BRICK_ROWS * pitch + ra + di];
+          const double pxb = s_brick[rb + di], pyb = s_brick[BRICK_ROWS * pitch + rb + di],
+                       pzb = s_brick[2 * BRICK_ROWS * pitch + rb + di];
+          ya0 += av[0] * pxa;
+          yb0 += av[0] * pxb;
+          ya0 += av[1] * pya;
+          yb0 += av[1] * pyb;
+          ya0 += av[2] * pza;
+          yb0 += av[2] * pzb;
+          ya1 += av[3] * pxa;
+          yb1 += av[3] * pxb;
+          ya1 += av[4] * pya;
+          yb1 += av[4] * pyb;
+          ya1 += av[5] * pza;
+          yb1 += av[5] * pzb;
+          ya2 += av[6] * pxa;
+          yb2 += av[6] * pxb;
+          ya2 += av[7] * pya;
+          yb2 += av[7] * pyb;
+          ya2 += av[8] * pza;
+          yb2 += av[8] * pzb;
         }
       }
-      const int n = nfix0 + fz * P.nxny + fy * P.nx + lx;
-      const int cb0 = ((fz + 1) * by_rows + (fy + 1)) * pitch + lx + xoff + 1;
-      Ap[n] = y0;
-      Ap[npad + n] = y1;
-      Ap[2 * npad + n] = y2;
-      red0 += s_brick[cb0] * y0;
-      red1 += s_brick[BRICK_ROWS * pitch + cb0] * y1;
-      red2 += s_brick[2 * BRICK_ROWS * pitch + cb0] * y2;
+      {
+        const int n = nfix0 + fza * P.nxny + fya * P.nx + lxa;
+        const int cb0 = ((fza + 1) * by_rows + (fya + 1)) * pitch + lxa + xoff + 1;
+        Ap[n] = ya0;
+        Ap[npad + n] = ya1;
+        Ap[2 * npad + n] = ya2;
+        red0 += s_brick[cb0] * ya0;
+        red1 += s_brick[BRICK_ROWS * pitch + cb0] * ya1;
+        red2 += s_brick[2 * BRICK_ROWS * pitch + cb0] * ya2;
+      }
+      if (two) {
+        const int n = nfix0 + fzb * P.nxny + fyb * P.nx + lxb;
+        const int cb0 = ((fzb + 1) * by_rows + (fyb + 1)) * pitch + lxb + xoff + 1;
+        Ap[n] = yb0;
+        Ap[npad + n] = yb1;
+        Ap[2 * npad + n] = yb2;
+        red0 += s_brick[cb0] * yb0;
+        red1 += s_brick[BRICK_ROWS * pitch + cb0] * yb1;
+        red2 += s_brick[2 * BRICK_ROWS * pitch + cb0] * yb2;
+      }
     }
     __syncwarp();
 
@@ -2191,7 +2222,7 @@ struct mgpu_ctx {
   int tile2_smem = 0;     // bytes of one brick
   int4 *d_tiles2 = nullptr;
   int *d_chunk_pure2 = nullptr, *d_fix_ptr2 = nullptr;
-  int2 *d_fix2 = nullptr;
+  int4 *d_fix2 = nullptr;
   int *d_elem_type = nullptr;
   double *d_ke = nullptr;
   double *d_be = nullptr;    // element residual scratch of assembly_rhs: [be_chunk][24][nelem_pad]
@@ -2768,10 +2799,11 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
                 for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y_a, z0, 1));
             t2.ntiles = (int)tiles.size();
             std::vector<int> chunk_pure((size_t)P.niz * P.niy * t2.nchunk, 0), fix_ptr(t2.ntiles + 1, 0);
-            std::vector<int2> fix;
+            std::vector<int4> tasks;
             for (int tile = 0; tile < t2.ntiles; ++tile) {
               const int4 td = tiles[tile];
-              fix_ptr[tile] = (int)fix.size();
+              std::vector<int2> fix;
+              fix_ptr[tile] = (int)tasks.size();
               const int ny_t = td.w ? TILE_Z : TILE_Y, nz_t = td.w ? TILE_Y : TILE_Z;
               for (int rz = 0; rz < nz_t; ++rz)
                 for (int ry = 0; ry < ny_t; ++ry)
@@ -2796,16 +2828,30 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
                       }
                     chunk_pure[((size_t)kk * P.niy + jj) * t2.nchunk + cc] = pure | (mask << 8);
                   }
+              // lanes of a warp take consecutive entries: sorted by row-block id, neighbouring lanes fetch the same
+              // row block (the loads of a fix-up round are bound by the distinct 32-B sectors a warp touches)
+              std::stable_sort(fix.begin(), fix.end(), [](const int2 &a, const int2 &b) { return a.y < b.y; });
+              // tasks: two nodes with the same row block share one task (one set of row-block loads)
+              for (size_t q = 0; q < fix.size();) {
+                if (q + 1 < fix.size() && fix[q + 1].y == fix[q].y) {
+                  tasks.push_back(make_int4(fix[q].x, fix[q + 1].x, fix[q].y, 0));
+                  q += 2;
+                } else {
+                  tasks.push_back(make_int4(fix[q].x, -1, fix[q].y, 0));
+                  q += 1;
+                }
+              }
             }
-            fix_ptr[t2.ntiles] = (int)fix.size();
+            fix_ptr[t2.ntiles] = (int)tasks.size();
             CK(cudaMalloc(&c->d_tiles2, sizeof(int4) * tiles.size()));
             CK(cudaMemcpy(c->d_tiles2, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice));
             CK(cudaMalloc(&c->d_chunk_pure2, sizeof(int) * chunk_pure.size()));
             CK(cudaMemcpy(c->d_chunk_pure2, chunk_pure.data(), sizeof(int) * chunk_pure.size(), cudaMemcpyHostToDevice));
             CK(cudaMalloc(&c->d_fix_ptr2, sizeof(int) * fix_ptr.size()));
             CK(cudaMemcpy(c->d_fix_ptr2, fix_ptr.data(), sizeof(int) * fix_ptr.size(), cudaMemcpyHostToDevice));
-            CK(cudaMalloc(&c->d_fix2, sizeof(int2) * std::max<size_t>(fix.size(), 1)));
-            if (!fix.empty()) CK(cudaMemcpy(c->d_fix2, fix.data(), sizeof(int2) * fix.size(), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&c->d_fix2, sizeof(int4) * std::max<size_t>(tasks.size(), 1)));
+            if (!tasks.empty())
+              CK(cudaMemcpy(c->d_fix2, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice));
             t2.tiles = c->d_tiles2;
             t2.chunk_pure = c->d_chunk_pure2;
             t2.fix_ptr = c->d_fix_ptr2;

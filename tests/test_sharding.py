@@ -100,3 +100,24 @@ def test_halo_exchange_pattern_gloo(tmp_path, world):
     port = 31000 + (os.getpid() % 2000) + world
     mp.spawn(_halo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert np.load(tmp_path / "halo_ok.npy")[0] == 1.0
+
+
+def test_balanced_ranges_cost_aware():
+    """(f) rank 4: contiguous cost-aware shards (test/mpi-load-balance.cpp:56-73: 25 % non-linear GPs cost 3-5x)."""
+    from micropp_b200.sharding import balanced_ranges, gp_range
+    # equal costs => the reference drivers' rule
+    for ngp, nproc in ((16, 4), (10, 3), (7, 8)):
+        got = balanced_ranges([5] * ngp, nproc)
+        assert [e - b for b, e in got if e > b] == [gp_range(ngp, nproc, r)[1] - gp_range(ngp, nproc, r)[0]
+                                                   for r in range(nproc) if gp_range(ngp, nproc, r)[1] > gp_range(ngp, nproc, r)[0]] \
+            or max(e - b for b, e in got) <= -(-ngp // nproc)
+        assert got[0][0] == 0 and max(e for _, e in got) == ngp
+    # the reference's imbalance scenario: the first quarter of the GPs is non-linear and 4x as expensive
+    costs = [400] * 16 + [100] * 48
+    parts = balanced_ranges(costs, 4)
+    assert len(parts) == 4 and parts[0][0] == 0 and parts[-1][1] == 64
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(3))
+    load = [sum(costs[b:e]) for b, e in parts]
+    naive = [sum(costs[gp_range(64, 4, r)[0]:gp_range(64, 4, r)[1]]) for r in range(4)]
+    assert max(load) < 0.55 * max(naive)          # 6400 on rank 0 with the plain rule, about 2800 balanced
+    assert max(load) <= 1.15 * sum(costs) / 4 + max(costs)
