@@ -591,7 +591,9 @@ __global__ void __launch_bounds__(NT)
   for (int q = threadIdx.x; q < GN * NPLANE; q += NT) s_acc[q] = 0.0;
   __syncthreads();
 
-  const int ln = threadIdx.x >> 3, c = threadIdx.x & 7;
+  // element-major thread order: the 16 lanes of a half-warp hold the SAME corner element of 16 x-consecutive nodes,
+  // i.e. 16 consecutive elements => their tangent loads are 128-B segments (node-major order: 8 segments of 32 B)
+  const int ln = threadIdx.x % GN, c = threadIdx.x / GN;
   const int m = blockIdx.x * GN + ln;  // interior-node index
   int i = 0, j = 0, k = 0;
   const bool work = m < P.nint;

@@ -373,3 +373,35 @@ def test_vtu_output(mpp, refpy, tmp_path, case, n, steps):
     finally:
         os.chdir(cwd)
     assert _vtu_arrays(tmp_path / "micropp-42-3.vtu")[1]["displ"].shape == ao["displ"].shape
+
+
+# ---------------------------------------------------------------- the bench workloads themselves vs the reference
+def test_bench_elastic30_against_reference(mpp, refpy):
+    """BASELINE configs[1] at FULL size (30^3, sphere, contrast 10, bench.py's seeded strains), three Gauss points
+    through the default product path (implicit operator, TMA-tiled SpMV, CUDA graphs) against the compiled reference:
+    stress to 1e-8 (north star), CG iterations +-1."""
+    import bench
+    wl = bench.WORKLOADS["elastic30"]
+    ngp = 3
+    eps = bench.strains_for("elastic30", 1024, 0, 0)[:ngp]
+    g = mpp.Micropp3(mpp.default_params(size=(30, 30, 30), ngp=ngp, **wl["params"]))
+    r = refpy.RefMicropp(refpy.default_params(size=(30, 30, 30), ngp=ngp, **wl["params"]))
+    assert g.implicit_kernel() == 3          # k_spmv_dot_tmac is what the bench measures
+    hg, hr = run_history(g, [eps]), run_history(r, [eps])
+    compare_histories(hg, hr, newton_budget=1)
+    assert 60 <= hg[0]["cost"][0] <= 90      # SURVEY 8d: about 75 CG iterations at 30^3, contrast 10
+
+
+def test_bench_damage_workload_against_reference(mpp, refpy):
+    """BASELINE configs[2] (damage matrix + elastic sphere, nr_max_its = 12, bench.py's load path) at 20^3 -- the
+    largest size the serial reference finishes in seconds -- over the load steps where the Gauss points turn
+    non-linear: stress to 1e-8, same non-linear / converged flags, CG iterations +-1 per Newton step."""
+    import bench
+    wl = bench.WORKLOADS["damage50"]
+    ngp = 2
+    g = mpp.Micropp3(mpp.default_params(size=(20, 20, 20), ngp=ngp, **wl["params"]))
+    r = refpy.RefMicropp(refpy.default_params(size=(20, 20, 20), ngp=ngp, **wl["params"]))
+    path = [bench.strains_for("damage50", 512, 0, k)[[3, 200]] for k in range(7)]
+    hg, hr = run_history(g, path), run_history(r, path)
+    compare_histories(hg, hr, newton_budget=12)
+    assert any(hg[-1]["nl"])                 # the path does reach the damage branch
