@@ -405,3 +405,24 @@ def test_bench_damage_workload_against_reference(mpp, refpy):
     hg, hr = run_history(g, path), run_history(r, path)
     compare_histories(hg, hr, newton_budget=12)
     assert any(hg[-1]["nl"])                 # the path does reach the damage branch
+
+
+@pytest.mark.parametrize("case,steps", [("damage_sphere", 7), ("elastic_sphere", 2), ("plastic_layer", 5)])
+def test_multi_wave_equals_single_wave(mpp, monkeypatch, case, steps):
+    """More Gauss points than resident slots (MICROPP_WAVE caps the wave; at BASELINE sizes 4096 damage RVEs of 50^3 do
+    not fit one GPU at once): the Gauss points are processed wave by wave with their FE state parked in HBM between
+    waves -- results, costs and flags must be bit-identical to the all-resident run."""
+    ngp = 7
+    kw = dict(ngp=ngp, lin_stress=False, calc_ctan_lin=False, nr_max_its=12)
+    path = load_path(ngp, steps, 99, comp=(1 if case == "plastic_layer" else 0),
+                     eps_max=(1.0 if case == "plastic_layer" else 0.1))
+    monkeypatch.setenv("MICROPP_WAVE", "3")
+    a = mpp.Micropp3(mk(mpp, case, 7, **kw))
+    assert a.wave_size() == 3
+    monkeypatch.delenv("MICROPP_WAVE")
+    b = mpp.Micropp3(mk(mpp, case, 7, **kw))
+    assert b.wave_size() >= ngp
+    ha, hb = run_history(a, path), run_history(b, path)
+    for x, y in zip(ha, hb):
+        assert np.array_equal(x["sig"], y["sig"])
+        assert x["cost"] == y["cost"] and x["nl"] == y["nl"] and x["conv"] == y["conv"]
