@@ -389,6 +389,14 @@ def main():
             r = {"kernel": "k_spmv_dot (DPCG SpMV + p.Ap, one assembled ELL matrix per RVE)", "bound": "hbm",
                  "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                  "traffic": None, "achieved_664": b_664 * apps / sec / 1e9, "bytes_per_rve_application": b_alg}
+        # the DPCG vector kernels (cg_update + cg_pupdate, HBM-bound streams; cg_init / cg_finish / u += du are in the
+        # same timer but run once per Newton step): bytes per node and iteration from DESIGN.md section 5
+        vec_b = (76.0 + 124.0 if implicit_kernel >= 0 else 120.0 + 120.0) * n ** 3
+        vec_sec = max(prof["cg_vec_ms"], 1e-9) * 1e-3
+        common["dpcg_vector_kernels"] = {"bound": "hbm", "achieved": vec_b * apps / vec_sec / 1e9, "peak": peak,
+                                         "unit": "GB/s", "frac": vec_b * apps / vec_sec / 1e9 / peak,
+                                         "bytes_per_rve_iteration": vec_b,
+                                         "share_of_step": prof["cg_vec_ms"] / max(prof_ms, 1e-9)}
         r.update(common)
         tr = ROOT / "profiles" / "spmv_traffic.json"  # dram bytes per RVE application from the committed ncu captures
         if tr.exists():

@@ -142,6 +142,22 @@ int mgpu_newton_step_graph(mgpu_ctx *, int n_active, int use_shared);
 /* ---- slab mode (one RVE split in z-slabs over several GPUs): the caller all-reduces the slab-local sums between a
    reducing kernel and its scalar tail, and exchanges the halo planes of p before every SpMV ---- */
 void mgpu_tail(mgpu_ctx *, int which_list, int n, int kind /*0 rhs,1 cg_init,2 spmv,3 cg_update,4 ave_stress*/, int mode);
+/* ---- slab mode over peer memory (NVLink P2P; no collective library in the DPCG loop) ----
+   Every rank owns a mailbox that all ranks map (mgpu_ipc_export / mgpu_ipc_open); slab-local sums are posted there with
+   an epoch and summed in rank order by every rank's tail kernel; halo planes of p are pulled from the neighbours'
+   vectors once their owner has published the epoch of its last p update.  All device-side waits are bounded. */
+void *mgpu_slab_mail(mgpu_ctx *);
+void mgpu_ipc_export(void *devptr, char *handle64);
+void *mgpu_ipc_open(int device, const char *handle64);
+void mgpu_ipc_close(void *mapped);
+void mgpu_slab_link(mgpu_ctx *, int rank, int size, void *const *mails, const void *p_lo, long long lo_off,
+                    long long lo_npad, const void *p_hi, long long hi_off, long long hi_npad);
+void mgpu_slab_publish_p(mgpu_ctx *);
+void mgpu_slab_halo_pull(mgpu_ctx *);
+void mgpu_slab_post(mgpu_ctx *, int k);
+void mgpu_slab_gather_tail(mgpu_ctx *, int which_list, int k, int kind, int mode); /* kind / mode as mgpu_tail */
+int mgpu_slab_error(mgpu_ctx *);  /* != 0: a wait for a peer timed out (syncs) */
+void mgpu_slab_cg_iteration(mgpu_ctx *, int which_list, int op);
 /* raw device pointers for the exchange: which 0..5 = b,du,Ap,p,u,r of slot 0 ([3][nn_pad]); 10 = slab sums
    ([W][8] doubles); 11 = averaged stress ([W][6]) */
 void *mgpu_dev_ptr(mgpu_ctx *, int which);

@@ -2125,6 +2125,113 @@ __global__ void k_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTab
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Slab mode over PEER MEMORY (NVLink P2P): the cross-rank steps of a DPCG iteration without any NCCL call.
+//  * every rank owns a small mailbox (SlabMail) that all ranks map (cudaIpc): the slab-local sums of a reducing kernel
+//    are posted there with an epoch number (st.release.sys); the tail kernel of every rank waits for the epoch of
+//    every mailbox (ld.acquire.sys), adds the partial sums in RANK ORDER (identical bits on all ranks) and runs the
+//    reference's scalar logic -- an all-reduce of <= 6 doubles costs two tiny kernels instead of a collective;
+//  * the halo planes of p are PULLED from the neighbours' vectors by k_slab_halo_pull once the neighbour has
+//    published the epoch of its last p update.
+// Write-after-read safety needs no extra flag: a rank overwrites p (next p update) only after the tail of the
+// following reduction, which cannot complete before every neighbour has posted its partial sum, i.e. has finished
+// the SpMV that followed its pull.  Two mailbox buffers (epoch parity) are enough for the same reason.
+// All waits are bounded (about 2 s): a lost rank raises SlabMail::error instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+struct SlabMail {
+  double red[2][8];
+  unsigned long long red_epoch, p_epoch;
+  int error, pad;
+};
+constexpr int SLAB_MAX_RANKS = 16;
+struct SlabPeers {
+  SlabMail *mail[SLAB_MAX_RANKS];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long epoch) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < epoch) {
+    if (clock64() - t0 > 4000000000ll) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+__global__ void k_slab_publish_p(SlabMail *mail, unsigned long long epoch) {
+  __threadfence_system();
+  st_release_sys(&mail->p_epoch, epoch);
+}
+
+// blockIdx.y = 0: low halo plane <- neighbour below, 1: high halo plane <- neighbour above
+__global__ void __launch_bounds__(NT)
+    k_slab_halo_pull(const __grid_constant__ MeshConst P, double *p_own, SlabMail *own, const double *p_lo,
+                     long long lo_off, long long lo_npad, const SlabMail *mail_lo, const double *p_hi, long long hi_off,
+                     long long hi_npad, const SlabMail *mail_hi, unsigned long long epoch) {
+  const bool hi = blockIdx.y == 1;
+  const double *src = hi ? p_hi : p_lo;
+  if (!src) return;
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = spin_until(hi ? &mail_hi->p_epoch : &mail_lo->p_epoch, epoch);
+    if (!ok) own->error = 1;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const long long off = hi ? hi_off : lo_off, npad = hi ? hi_npad : lo_npad;
+  double *dst = p_own + (size_t)(hi ? P.nz - 1 : 0) * P.nxny;
+  for (int i = blockIdx.x * NT + threadIdx.x; i < P.nxny; i += gridDim.x * NT) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) dst[(size_t)d * P.nn_pad + i] = __ldcv(src + (size_t)d * npad + off + i);
+  }
+}
+
+__global__ void k_slab_post(const double *red, SlabMail *mail, int k, unsigned long long epoch) {
+  if (threadIdx.x != 0) return;
+  for (int q = 0; q < k; ++q) mail->red[epoch & 1][q] = red[q];
+  __threadfence_system();
+  st_release_sys(&mail->red_epoch, epoch);
+}
+
+// sum of the posted slab sums in rank order, then the scalar tail (k_tail) on this rank
+__global__ void k_slab_gather_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
+                                   const __grid_constant__ SlabPeers peers, SlabMail *own, int nranks, int k,
+                                   unsigned long long epoch, int kind, int mode) {
+  const int slot = slot_of(L);
+  if (slot < 0 || threadIdx.x != 0) return;
+  double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < nranks; ++r) {
+    if (!spin_until(&peers.mail[r]->red_epoch, epoch)) own->error = 1;
+    for (int q = 0; q < k; ++q) tot[q] += __ldcv(&peers.mail[r]->red[epoch & 1][q]);
+  }
+  double *red = T.red + slot * 8;
+  for (int q = 0; q < k; ++q) red[q] = tot[q];
+  mgpu_slot_state *st = &T.state[slot];
+  switch (kind) {
+    case 0:
+      if (mode == 1 && !st->nr_active) return;
+      tail_rhs(P, st, red[0], mode);
+      break;
+    case 1: tail_cg_init(P, st, red[0], red[1]); break;
+    case 2:
+      if (st->cg_active) tail_spmv(st, red[0]);
+      break;
+    case 3:
+      if (st->cg_active) tail_cg_update(P, st, red[0], red[1]);
+      break;
+    default:
+      for (int q = 0; q < 6; ++q) T.stress[slot * 6 + q] = red[q] / 1.0;
+      break;
+  }
+}
+
 __global__ void k_clear_nl(const int *__restrict__ list, int n, SlotTables T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) T.state[list[i]].nl_flag = 0;
@@ -2219,6 +2326,13 @@ struct mgpu_ctx {
   int tma_smem = 0;
   PureRows pure_rows;     // host copy of row blocks 0..2 (kernel parameter of k_spmv_dot_tmac)
   int tma_variant = 0;    // 0: k_spmv_dot_tma (row blocks in shared memory); v >= 1: k_spmv_dot_tmac variant v
+  // slab mode over peer memory (mgpu_slab_link)
+  SlabMail *slab_mail = nullptr;
+  SlabPeers slab_peers{};
+  int slab_rank = -1, slab_size = 0;
+  unsigned long long slab_ep_p = 0, slab_ep_red = 0;
+  const double *slab_p_lo = nullptr, *slab_p_hi = nullptr;
+  long long slab_lo_off = 0, slab_lo_npad = 0, slab_hi_off = 0, slab_hi_npad = 0;
   TileInfo2 tile2;        // tiling of k_spmv_dot_tmac (7 or 8 nodes per thread, two lane shapes)
   CUtensorMap tmap_a, tmap_b;  // V.p with the boxes of lane shape 0 (pitch x 10 x 6) and 1 (pitch x 6 x 10)
   int tile2_smem = 0;     // bytes of one brick
@@ -2939,6 +3053,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   if (c->d_chunk_id) cudaFree(c->d_chunk_id);
   if (c->d_chunk_pure) cudaFree(c->d_chunk_pure);
   if (c->d_fix_ptr) cudaFree(c->d_fix_ptr);
+  if (c->slab_mail) cudaFree(c->slab_mail);
   if (c->d_tiles2) cudaFree(c->d_tiles2);
   if (c->d_chunk_pure2) cudaFree(c->d_chunk_pure2);
   if (c->d_fix_ptr2) cudaFree(c->d_fix_ptr2);
@@ -3453,6 +3568,100 @@ extern "C" void *mgpu_dev_ptr(mgpu_ctx *c, int which) {
   return vec_of(c, which);
 }
 extern "C" void *mgpu_stream(mgpu_ctx *c) { return (void *)c->stream; }
+
+// ---- slab mode over peer memory ------------------------------------------------------------------
+extern "C" {
+// this rank's mailbox (device memory, zeroed); export it with mgpu_ipc_export
+void *mgpu_slab_mail(mgpu_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  if (!c->slab_mail) {
+    CK(cudaMalloc(&c->slab_mail, sizeof(SlabMail)));
+    CK(cudaMemset(c->slab_mail, 0, sizeof(SlabMail)));
+  }
+  return c->slab_mail;
+}
+// 64-byte CUDA IPC handle of a device allocation of this process / mapping of another process' handle
+void mgpu_ipc_export(void *devptr, char *handle64) {
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, devptr));
+  memcpy(handle64, &h, sizeof(h));
+}
+void *mgpu_ipc_open(int device, const char *handle64) {
+  CK(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void *p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return p;
+}
+void mgpu_ipc_close(void *p) { cudaIpcCloseMemHandle(p); }
+// mails[r]: mailbox of rank r as mapped here (r == rank: the own one); p_lo / p_hi: the neighbours' p vectors
+// (null at the ends), *_off: offset (doubles, component 0) of the neighbour's owned plane next to the cut,
+// *_npad: the neighbour's component stride
+void mgpu_slab_link(mgpu_ctx *c, int rank, int size, void *const *mails, const void *p_lo, long long lo_off,
+                    long long lo_npad, const void *p_hi, long long hi_off, long long hi_npad) {
+  if (size > SLAB_MAX_RANKS) {
+    fprintf(stderr, "micropp-b200: at most %d slabs\n", SLAB_MAX_RANKS);
+    abort();
+  }
+  mgpu_slab_mail(c);
+  c->slab_rank = rank;
+  c->slab_size = size;
+  for (int r = 0; r < size; ++r) c->slab_peers.mail[r] = (SlabMail *)mails[r];
+  c->slab_p_lo = (const double *)p_lo;
+  c->slab_p_hi = (const double *)p_hi;
+  c->slab_lo_off = lo_off;
+  c->slab_lo_npad = lo_npad;
+  c->slab_hi_off = hi_off;
+  c->slab_hi_npad = hi_npad;
+  c->slab_ep_p = c->slab_ep_red = 0;
+}
+void mgpu_slab_publish_p(mgpu_ctx *c) {
+  c->launches++;
+  k_slab_publish_p<<<1, 1, 0, c->stream>>>(c->slab_mail, ++c->slab_ep_p);
+  CK(cudaGetLastError());
+}
+void mgpu_slab_halo_pull(mgpu_ctx *c) {
+  c->launches++;
+  const int nb = std::min(64, (c->mc.nxny + NT - 1) / NT);
+  k_slab_halo_pull<<<dim3(nb, 2), NT, 0, c->stream>>>(
+      c->mc, c->V.p, c->slab_mail, c->slab_p_lo, c->slab_lo_off, c->slab_lo_npad,
+      c->slab_rank > 0 ? c->slab_peers.mail[c->slab_rank - 1] : nullptr, c->slab_p_hi, c->slab_hi_off, c->slab_hi_npad,
+      c->slab_rank + 1 < c->slab_size ? c->slab_peers.mail[c->slab_rank + 1] : nullptr, c->slab_ep_p);
+  CK(cudaGetLastError());
+}
+void mgpu_slab_post(mgpu_ctx *c, int k) {
+  c->launches++;
+  k_slab_post<<<1, 32, 0, c->stream>>>(c->T.red, c->slab_mail, k, ++c->slab_ep_red);
+  CK(cudaGetLastError());
+}
+void mgpu_slab_gather_tail(mgpu_ctx *c, int l, int k, int kind, int mode) {
+  c->launches++;
+  k_slab_gather_tail<<<dim3(1, 1), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
+                                                      c->slab_size, k, c->slab_ep_red, kind, mode);
+  CK(cudaGetLastError());
+}
+int mgpu_slab_error(mgpu_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  SlabMail m;
+  CK(cudaMemcpy(&m, c->slab_mail, sizeof(m), cudaMemcpyDeviceToHost));
+  return m.error;
+}
+// One DPCG iteration of this rank's slab (multi-process mode: every rank calls it; no host synchronisation):
+// halo pull -> SpMV -> post/tail(p.Ap) -> r, z update -> post/tail(z.z, r.z) -> p, x update -> publish p
+void mgpu_slab_cg_iteration(mgpu_ctx *c, int l, int op) {
+  mgpu_slab_halo_pull(c);
+  mgpu_cg_spmv_dot(c, l, 1, op);
+  mgpu_slab_post(c, 1);
+  mgpu_slab_gather_tail(c, l, 1, 2, 0);
+  mgpu_cg_update(c, l, 1);
+  mgpu_slab_post(c, 2);
+  mgpu_slab_gather_tail(c, l, 2, 3, 0);
+  mgpu_cg_pupdate(c, l, 1);
+  mgpu_slab_publish_p(c);
+}
+}
 
 // ---- results ----------------------------------------------------------------------------------
 void mgpu_fetch_state(mgpu_ctx *c, int n, const int *slots, mgpu_slot_state *out) {

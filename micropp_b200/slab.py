@@ -5,10 +5,12 @@ nx x ny x nz RVE are divided into contiguous z-ranges, one per rank (one process
 sm_100a kernels as the batched path on its local planes plus one halo plane towards each neighbour
 (`micropp3x_slab_create`, include/micropp_b200_ext.h); the only differences are
 
-  * before every SpMV the halo planes of the search direction p are exchanged with the two neighbours
-    (3 * nx * ny doubles each way; NCCL send/recv through torch.distributed),
+  * before every SpMV the halo planes of the search direction p are fetched from the two neighbours
+    (3 * nx * ny doubles each way): by default PULLED straight from the neighbour's vector over NVLink peer memory
+    (CUDA IPC mapping, device-side epoch flags; `exchange="peer"`), or by NCCL send/recv (`exchange="nccl"`),
   * the three dot products of a DPCG iteration (p.Ap, then z.z and r.z), the residual norm of a Newton step and
-    the six stress sums are slab-local sums that are all-reduced (NCCL) before their scalar "tail"
+    the six stress sums are slab-local sums that are summed over the ranks -- through peer-mapped mailboxes, in rank
+    order, inside the tail kernel itself (peer mode), or by an NCCL all-reduce -- before their scalar "tail"
     (alpha, beta, convergence tests: the reference's logic of src/ell.cpp:93-119 and src/solve.cpp:43-47) runs on
     every rank -- so all ranks take identical decisions.
 
@@ -89,6 +91,14 @@ def _bind(lib):
         "mgpu_fetch_stress": (None, [V, C.c_int, _ip, _dp]),
         "mgpu_dev_ptr": (V, [V, C.c_int]), "mgpu_stream": (V, [V]), "mgpu_implicit": (C.c_int, [V]),
         "mgpu_stage_get_u": (None, [V, C.c_int, _dp]),
+        # peer-memory exchange (NVLink P2P, no collective library inside the DPCG loop)
+        "mgpu_slab_mail": (V, [V]), "mgpu_ipc_export": (None, [V, C.c_char_p]),
+        "mgpu_ipc_open": (V, [C.c_int, C.c_char_p]), "mgpu_ipc_close": (None, [V]),
+        "mgpu_slab_link": (None, [V, C.c_int, C.c_int, C.POINTER(V), V, C.c_longlong, C.c_longlong, V, C.c_longlong,
+                                  C.c_longlong]),
+        "mgpu_slab_publish_p": (None, [V]), "mgpu_slab_halo_pull": (None, [V]), "mgpu_slab_post": (None, [V, C.c_int]),
+        "mgpu_slab_gather_tail": (None, [V, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "mgpu_slab_error": (C.c_int, [V]), "mgpu_slab_cg_iteration": (None, [V, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -141,7 +151,8 @@ class SlabRVE:
 
     L0 = 0  # device slot list used for every launch (one slot per slab)
 
-    def __init__(self, params: dict, *, world=None, nslabs: int = 1, device: int = 0, cg_chunk: int = 8):
+    def __init__(self, params: dict, *, world=None, nslabs: int = 1, device: int = 0, cg_chunk: int = 8,
+                 exchange: str = "peer"):
         import torch
         self.torch = torch
         self.lib = load()
@@ -179,6 +190,54 @@ class SlabRVE:
         self.allreduces = 0
         # DPCG operator: 3 = implicit operator of an all-elastic RVE (no assembled matrix), 0 = the slab's own ELL matrix
         self.op = 3 if all(self.lib.mgpu_implicit(s.ctx) for s in self.slabs) else 0
+        # "peer": halo planes pulled from the neighbours' memory and dot products summed through peer-mapped
+        # mailboxes (NVLink P2P, device-side flags); "nccl": send/recv + all-reduce through torch.distributed
+        self.exchange = exchange
+        self._mapped = []
+        if exchange == "peer":
+            self._link_peers(device)
+
+    def _link_peers(self, device):
+        lib = self.lib
+        V = C.c_void_p
+        if self.world is None:   # every slab lives in this process: plain device pointers
+            mails = [lib.mgpu_slab_mail(s.ctx) for s in self.slabs]
+            pptr = [lib.mgpu_dev_ptr(s.ctx, 3) for s in self.slabs]
+            info = [(s.nzl, s.nn_pad) for s in self.slabs]
+            mine = range(len(self.slabs))
+        else:                    # one slab per process: CUDA IPC handles travel through the process group
+            s = self.slabs[0]
+            hm, hp = C.create_string_buffer(64), C.create_string_buffer(64)
+            lib.mgpu_ipc_export(lib.mgpu_slab_mail(s.ctx), hm)
+            lib.mgpu_ipc_export(lib.mgpu_dev_ptr(s.ctx, 3), hp)
+            allinfo = [None] * self.size
+            self.dist.all_gather_object(allinfo, (hm.raw, hp.raw, s.nzl, s.nn_pad))
+            mails, pptr, info = [], [], []
+            for r, (m_raw, p_raw, nzl, npad) in enumerate(allinfo):
+                info.append((nzl, npad))
+                if r == self.rank:
+                    mails.append(lib.mgpu_slab_mail(s.ctx))
+                    pptr.append(lib.mgpu_dev_ptr(s.ctx, 3))
+                    continue
+                mails.append(lib.mgpu_ipc_open(device, m_raw))
+                self._mapped.append(mails[-1])
+                if abs(r - self.rank) == 1:
+                    pptr.append(lib.mgpu_ipc_open(device, p_raw))
+                    self._mapped.append(pptr[-1])
+                else:
+                    pptr.append(None)
+            mine = [self.rank]
+        arr = (V * self.size)(*[V(m) for m in mails])
+        for i, r in enumerate(mine):
+            s = self.slabs[i]
+            lo = pptr[r - 1] if r > 0 else None
+            hi = pptr[r + 1] if r + 1 < self.size else None
+            lo_off = (info[r - 1][0] - 2) * s.nxny if r > 0 else 0          # the lower neighbour's top owned plane
+            hi_off = 1 * s.nxny if r + 1 < self.size else 0                  # the upper neighbour's bottom owned plane
+            lib.mgpu_slab_link(s.ctx, r, self.size, arr, lo, lo_off, info[r - 1][1] if r > 0 else 0, hi, hi_off,
+                               info[r + 1][1] if r + 1 < self.size else 0)
+        if self.world is not None:
+            self.dist.barrier()
 
     # ------------------------------------------------------------------ communication
     def _allreduce(self, k: int):
@@ -202,6 +261,11 @@ class SlabRVE:
         """Halo planes of p <- the neighbour's adjacent owned plane."""
         torch = self.torch
         self.exchanges += 1
+        if self.exchange == "peer":
+            if self.world is None:
+                torch.cuda.synchronize()   # one process, one stream per slab: the publishes must have run
+            self._each(self.lib.mgpu_slab_halo_pull)
+            return
         if self.world is None:
             torch.cuda.synchronize()
             for a, b in zip(self.slabs[:-1], self.slabs[1:]):  # a below b
@@ -228,19 +292,37 @@ class SlabRVE:
     def _reduced(self, kernel, kargs, k, tail_kind, tail_mode=0):
         """reducing kernel -> all-reduce of its k slab-local sums -> scalar tail on every slab"""
         self._each(kernel, *kargs)
+        if self.exchange == "peer":
+            self.allreduces += 1
+            self._each(self.lib.mgpu_slab_post, k)
+            if self.world is None:
+                self.torch.cuda.synchronize()   # all posts of this process's slabs before any tail waits for them
+            self._each(self.lib.mgpu_slab_gather_tail, self.L0, k, tail_kind, tail_mode)
+            return
         self._allreduce(k)
         self._each(self.lib.mgpu_tail, self.L0, 1, tail_kind, tail_mode)
 
     # ------------------------------------------------------------------ solver
     def cg_solve(self):
         lib, L0 = self.lib, self.L0
+        peer = self.exchange == "peer"
         self._reduced(lib.mgpu_cg_init, (L0, 1, self.op), 2, 1)
+        if peer:
+            self._each(lib.mgpu_slab_publish_p)
         while self.slabs[0].state().cg_active:
             for _ in range(self.cg_chunk):
+                if peer and self.world is not None:
+                    # one call per iteration, nothing but kernel launches: the cross-rank steps are device-side
+                    self.exchanges += 1
+                    self.allreduces += 2
+                    lib.mgpu_slab_cg_iteration(self.slabs[0].ctx, L0, self.op)
+                    continue
                 self._exchange_p()
                 self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, self.op), 1, 2)
                 self._reduced(lib.mgpu_cg_update, (L0, 1), 2, 3)
                 self._each(lib.mgpu_cg_pupdate, L0, 1)
+                if peer:
+                    self._each(lib.mgpu_slab_publish_p)
         self._each(lib.mgpu_cg_finish, L0, 1)   # the deferred x += alpha p of the last iteration
 
     def homogenize(self, eps) -> dict:
@@ -283,7 +365,17 @@ class SlabRVE:
     def sync(self):
         self._each(self.lib.mgpu_sync)
 
+    def peer_error(self) -> int:
+        """!= 0: a device-side wait for a peer timed out (peer exchange only)."""
+        return max(int(self.lib.mgpu_slab_error(s.ctx)) for s in self.slabs) if self.exchange == "peer" else 0
+
     def close(self):
+        if self.world is not None and self.exchange == "peer" and self.slabs:
+            self.sync()
+            self.dist.barrier()          # nobody unmaps memory a neighbour may still read
+        for m in self._mapped:
+            self.lib.mgpu_ipc_close(m)
+        self._mapped = []
         for s in self.slabs:
             s.close()
         self.slabs = []

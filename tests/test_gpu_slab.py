@@ -13,8 +13,12 @@ from common import CASES, relerr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("dims,nslabs", [((10, 9, 12), 2), ((10, 9, 12), 3), ((12, 12, 12), 4), ((8, 8, 8), 1)])
-def test_slab_equals_single_domain(mpp, refpy, dims, nslabs):
+def test_slab_equals_single_domain(mpp, refpy, dims, nslabs, exchange):
+    """exchange="peer": halo planes pulled from the neighbour's vector and dot products summed through mailboxes with
+    device-side epoch flags (the NVLink P2P path; here all slabs sit on one GPU, so the "peer" pointers are local);
+    "nccl": the send/recv + all-reduce transport (device copies in this single-process mode)."""
     from micropp_b200.slab import SlabRVE
     kw = dict(size=dims, lin_stress=False, calc_ctan_lin=False, **CASES["elastic_sphere"])
     eps = np.array([1.0e-3, -0.4e-3, 0.2e-3, 0.6e-3, -0.3e-3, 0.1e-3])
@@ -24,8 +28,9 @@ def test_slab_equals_single_domain(mpp, refpy, dims, nslabs):
     s1, c1 = one.get_stress(0), one.get_cost(0)
     u1 = one.get_u(0, 1).reshape(-1, 3)
 
-    rve = SlabRVE(kw, nslabs=nslabs)
+    rve = SlabRVE(kw, nslabs=nslabs, exchange=exchange)
     out = rve.homogenize(eps)
+    assert rve.peer_error() == 0
     assert out["converged"] and abs(out["cg_its"] - c1) <= 1
     assert relerr(out["stress"], s1) < 1e-10
     assert relerr(rve.get_u(), u1) < 1e-8
@@ -49,6 +54,7 @@ def test_slab_damage_first_step(mpp):
     one.homogenize()
     rve = SlabRVE(kw, nslabs=3)
     out = rve.homogenize(eps)
+    assert rve.peer_error() == 0
     assert out["converged"] == one.has_converged(0)
     assert abs(out["cg_its"] - one.get_cost(0)) <= out["newton_its"]
     assert relerr(out["stress"], one.get_stress(0)) < 1e-8

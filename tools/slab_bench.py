@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--rve", type=int, default=200)
     ap.add_argument("--check", action="store_true", help="compare with the single-domain solver (n <= 60)")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="peer: NVLink P2P pulls + mailbox sums with device-side flags; nccl: send/recv + all-reduce")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -41,7 +43,7 @@ def main():
               lin_stress=False, calc_ctan_lin=False)
     eps = np.array([1e-3, 0, 0, 0, 0, 0.0])
     t0 = time.perf_counter()
-    rve = SlabRVE(kw, world=w, nslabs=1, device=lr)
+    rve = SlabRVE(kw, world=w, nslabs=1, device=lr, exchange=args.exchange)
     ctor = time.perf_counter() - t0
     times = []
     for _ in range(args.reps):
@@ -57,7 +59,8 @@ def main():
         times.append(float(t.item()))
     best = min(times)
     its = out["cg_its"]
-    line = {"config": f"single {n}^3 RVE, elastic sphere contrast 10, z-slabs", "n_gpus": world, "ms": best * 1e3,
+    line = {"config": f"single {n}^3 RVE, elastic sphere contrast 10, z-slabs", "n_gpus": world,
+            "exchange": args.exchange, "peer_error": rve.peer_error(), "ms": best * 1e3,
             "ms_all": [round(x * 1e3, 2) for x in times], "cg_its": its, "newton_its": out["newton_its"],
             "converged": out["converged"], "stress": [float(x) for x in out["stress"]],
             "cg_iteration_us": best * 1e6 / max(its, 1),
