@@ -158,6 +158,7 @@ void mgpu_slab_post(mgpu_ctx *, int k);
 void mgpu_slab_gather_tail(mgpu_ctx *, int which_list, int k, int kind, int mode); /* kind / mode as mgpu_tail */
 int mgpu_slab_error(mgpu_ctx *);  /* != 0: a wait for a peer timed out (syncs) */
 void mgpu_slab_cg_iteration(mgpu_ctx *, int which_list, int op);
+void mgpu_slab_cg_chunk(mgpu_ctx *, int which_list, int op, int iters); /* iters iterations as one CUDA graph launch */
 /* raw device pointers for the exchange: which 0..5 = b,du,Ap,p,u,r of slot 0 ([3][nn_pad]); 10 = slab sums
    ([W][8] doubles); 11 = averaged stress ([W][6]) */
 void *mgpu_dev_ptr(mgpu_ctx *, int which);

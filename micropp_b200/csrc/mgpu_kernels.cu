@@ -2140,7 +2140,9 @@ __global__ void k_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTab
 // ------------------------------------------------------------------------------------------------
 struct SlabMail {
   double red[2][8];
-  unsigned long long red_epoch, p_epoch;
+  unsigned long long red_epoch, p_epoch;  // published epochs (read by the peers)
+  unsigned long long red_local, p_local;  // the owner's own counters: the epochs live on the device, so a whole chunk
+                                          // of DPCG iterations is a replayable CUDA graph with constant arguments
   int error, pad;
 };
 constexpr int SLAB_MAX_RANKS = 16;
@@ -2165,7 +2167,8 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
   return true;
 }
 
-__global__ void k_slab_publish_p(SlabMail *mail, unsigned long long epoch) {
+__global__ void k_slab_publish_p(SlabMail *mail) {
+  const unsigned long long epoch = ++mail->p_local;
   __threadfence_system();
   st_release_sys(&mail->p_epoch, epoch);
 }
@@ -2174,12 +2177,13 @@ __global__ void k_slab_publish_p(SlabMail *mail, unsigned long long epoch) {
 __global__ void __launch_bounds__(NT)
     k_slab_halo_pull(const __grid_constant__ MeshConst P, double *p_own, SlabMail *own, const double *p_lo,
                      long long lo_off, long long lo_npad, const SlabMail *mail_lo, const double *p_hi, long long hi_off,
-                     long long hi_npad, const SlabMail *mail_hi, unsigned long long epoch) {
+                     long long hi_npad, const SlabMail *mail_hi) {
   const bool hi = blockIdx.y == 1;
   const double *src = hi ? p_hi : p_lo;
   if (!src) return;
   __shared__ int ok;
   if (threadIdx.x == 0) {
+    const unsigned long long epoch = own->p_local;  // as many publishes as this rank has done itself
     ok = spin_until(hi ? &mail_hi->p_epoch : &mail_lo->p_epoch, epoch);
     if (!ok) own->error = 1;
   }
@@ -2193,8 +2197,9 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
-__global__ void k_slab_post(const double *red, SlabMail *mail, int k, unsigned long long epoch) {
+__global__ void k_slab_post(const double *red, SlabMail *mail, int k) {
   if (threadIdx.x != 0) return;
+  const unsigned long long epoch = ++mail->red_local;
   for (int q = 0; q < k; ++q) mail->red[epoch & 1][q] = red[q];
   __threadfence_system();
   st_release_sys(&mail->red_epoch, epoch);
@@ -2203,9 +2208,10 @@ __global__ void k_slab_post(const double *red, SlabMail *mail, int k, unsigned l
 // sum of the posted slab sums in rank order, then the scalar tail (k_tail) on this rank
 __global__ void k_slab_gather_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                                    const __grid_constant__ SlabPeers peers, SlabMail *own, int nranks, int k,
-                                   unsigned long long epoch, int kind, int mode) {
+                                   int kind, int mode) {
   const int slot = slot_of(L);
   if (slot < 0 || threadIdx.x != 0) return;
+  const unsigned long long epoch = own->red_local;
   double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < nranks; ++r) {
     if (!spin_until(&peers.mail[r]->red_epoch, epoch)) own->error = 1;
@@ -2330,7 +2336,8 @@ struct mgpu_ctx {
   SlabMail *slab_mail = nullptr;
   SlabPeers slab_peers{};
   int slab_rank = -1, slab_size = 0;
-  unsigned long long slab_ep_p = 0, slab_ep_red = 0;
+  std::map<int, cudaGraphExec_t> slab_chunk_graphs;  // key: op * 1024 + iterations
+  int slab_launches_per_chunk = 0;
   const double *slab_p_lo = nullptr, *slab_p_hi = nullptr;
   long long slab_lo_off = 0, slab_lo_npad = 0, slab_hi_off = 0, slab_hi_npad = 0;
   TileInfo2 tile2;        // tiling of k_spmv_dot_tmac (7 or 8 nodes per thread, two lane shapes)
@@ -2448,6 +2455,15 @@ inline tmac_kernel_t tmac_kernel_tn(int variant, int cb) {
 }
 inline tmac_kernel_t tmac_kernel(int variant, int cb, int tn) {  // variant 1..N_TMAC
   return tn == 7 ? tmac_kernel_tn<7>(variant, cb) : tmac_kernel_tn<8>(variant, cb);
+}
+
+// Host -> device copy ORDERED WITH THE CONTEXT STREAM.  A plain cudaMemcpy from pageable memory may return before its
+// DMA has landed, and the legacy default stream it runs on is not ordered with the non-blocking context stream the
+// kernels use: a kernel launched right after it could read the old contents (seen as a rare wrong first operator
+// application in the tests).  The copy is enqueued on the context stream and waited for (the source may be a temporary).
+inline void h2d_sync(mgpu_ctx *c, void *dst, const void *src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
 }
 
 struct ProfScope {
@@ -2658,9 +2674,9 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   c->ngp = cfg->ngp;
 
   CK(cudaMalloc(&c->d_elem_type, sizeof(int) * std::max(P.nelem, 1)));
-  CK(cudaMemcpy(c->d_elem_type, cfg->elem_type, sizeof(int) * P.nelem, cudaMemcpyHostToDevice));
+  h2d_sync(c, c->d_elem_type, cfg->elem_type, sizeof(int) * P.nelem);
   CK(cudaMalloc(&c->d_ke, sizeof(double) * 3 * 576));
-  CK(cudaMemcpy(c->d_ke, cfg->ke_elastic, sizeof(double) * 3 * 576, cudaMemcpyHostToDevice));
+  h2d_sync(c, c->d_ke, cfg->ke_elastic, sizeof(double) * 3 * 576);
 
   // persistent displacement state u_n,u_k of every FE Gauss point
   const size_t vlen = (size_t)3 * P.nn_pad;
@@ -2768,8 +2784,8 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     CK(cudaMalloc(&d_rowid, sizeof(int) * P.nint_pad));
     CK(cudaMalloc(&d_rows, sizeof(double) * RB_LEN * c->nrows));
     CK(cudaMalloc(&d_rkinv, sizeof(double) * 3 * c->nrows));
-    CK(cudaMemcpy(d_codes, codes.data(), sizeof(int) * c->nrows, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_rowid, rowid.data(), sizeof(int) * P.nint_pad, cudaMemcpyHostToDevice));
+    h2d_sync(c, d_codes, codes.data(), sizeof(int) * c->nrows);
+    h2d_sync(c, d_rowid, rowid.data(), sizeof(int) * P.nint_pad);
     k_rows_build<<<(c->nrows + NT - 1) / NT, NT, 0, c->stream>>>(d_codes, c->nrows, d_rows, d_rkinv, c->d_ke);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -2847,17 +2863,17 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
       fix_ptr[ntiles] = (int)fix.size();
       c->nfix = (int)fix.size();
       CK(cudaMalloc(&c->d_chunk_pure, sizeof(int) * chunk_pure.size()));
-      CK(cudaMemcpy(c->d_chunk_pure, chunk_pure.data(), sizeof(int) * chunk_pure.size(), cudaMemcpyHostToDevice));
+      h2d_sync(c, c->d_chunk_pure, chunk_pure.data(), sizeof(int) * chunk_pure.size());
       CK(cudaMalloc(&c->d_fix_ptr, sizeof(int) * fix_ptr.size()));
-      CK(cudaMemcpy(c->d_fix_ptr, fix_ptr.data(), sizeof(int) * fix_ptr.size(), cudaMemcpyHostToDevice));
+      h2d_sync(c, c->d_fix_ptr, fix_ptr.data(), sizeof(int) * fix_ptr.size());
       CK(cudaMalloc(&c->d_fix, sizeof(int2) * std::max<size_t>(fix.size(), 1)));
-      if (!fix.empty()) CK(cudaMemcpy(c->d_fix, fix.data(), sizeof(int2) * fix.size(), cudaMemcpyHostToDevice));
+      if (!fix.empty()) h2d_sync(c, c->d_fix, fix.data(), sizeof(int2) * fix.size());
       ti.chunk_pure = c->d_chunk_pure;
       ti.fix_ptr = c->d_fix_ptr;
       ti.fix = c->d_fix;
     }
     CK(cudaMalloc(&c->d_chunk_id, sizeof(int) * chunk_id.size()));
-    CK(cudaMemcpy(c->d_chunk_id, chunk_id.data(), sizeof(int) * chunk_id.size(), cudaMemcpyHostToDevice));
+    h2d_sync(c, c->d_chunk_id, chunk_id.data(), sizeof(int) * chunk_id.size());
     ti.chunk_id = c->d_chunk_id;
     CK(cudaFuncSetAttribute(tile_kernel(ti.cb), cudaFuncAttributeMaxDynamicSharedMemorySize, c->tile_smem));
     c->imp_kernel = 1;
@@ -2960,14 +2976,14 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
             }
             fix_ptr[t2.ntiles] = (int)tasks.size();
             CK(cudaMalloc(&c->d_tiles2, sizeof(int4) * tiles.size()));
-            CK(cudaMemcpy(c->d_tiles2, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice));
+            h2d_sync(c, c->d_tiles2, tiles.data(), sizeof(int4) * tiles.size());
             CK(cudaMalloc(&c->d_chunk_pure2, sizeof(int) * chunk_pure.size()));
-            CK(cudaMemcpy(c->d_chunk_pure2, chunk_pure.data(), sizeof(int) * chunk_pure.size(), cudaMemcpyHostToDevice));
+            h2d_sync(c, c->d_chunk_pure2, chunk_pure.data(), sizeof(int) * chunk_pure.size());
             CK(cudaMalloc(&c->d_fix_ptr2, sizeof(int) * fix_ptr.size()));
-            CK(cudaMemcpy(c->d_fix_ptr2, fix_ptr.data(), sizeof(int) * fix_ptr.size(), cudaMemcpyHostToDevice));
+            h2d_sync(c, c->d_fix_ptr2, fix_ptr.data(), sizeof(int) * fix_ptr.size());
             CK(cudaMalloc(&c->d_fix2, sizeof(int4) * std::max<size_t>(tasks.size(), 1)));
             if (!tasks.empty())
-              CK(cudaMemcpy(c->d_fix2, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice));
+              h2d_sync(c, c->d_fix2, tasks.data(), sizeof(int4) * tasks.size());
             t2.tiles = c->d_tiles2;
             t2.chunk_pure = c->d_chunk_pure2;
             t2.fix_ptr = c->d_fix_ptr2;
@@ -3031,6 +3047,7 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   CK(cudaFuncSetAttribute(k_asm_mat_general, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)(GN * NPLANE * sizeof(double))));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaDeviceSynchronize());  // the cudaMemset calls above ran on the legacy stream, which the context stream ignores
   return c;
 }
 
@@ -3053,6 +3070,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   if (c->d_chunk_id) cudaFree(c->d_chunk_id);
   if (c->d_chunk_pure) cudaFree(c->d_chunk_pure);
   if (c->d_fix_ptr) cudaFree(c->d_fix_ptr);
+  for (auto &kv : c->slab_chunk_graphs) cudaGraphExecDestroy(kv.second);
   if (c->slab_mail) cudaFree(c->slab_mail);
   if (c->d_tiles2) cudaFree(c->d_tiles2);
   if (c->d_chunk_pure2) cudaFree(c->d_chunk_pure2);
@@ -3122,7 +3140,7 @@ void mgpu_gp_set_u(mgpu_ctx *c, int gp, int which, const double *host_aos) {
   std::vector<double> tmp;
   aos_to_soa(c, host_aos, tmp);
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(which ? c->u_k[gp] : c->u_n[gp], tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h2d_sync(c, which ? c->u_k[gp] : c->u_n[gp], tmp.data(), tmp.size() * sizeof(double));
 }
 void mgpu_gp_get_vars(mgpu_ctx *c, int gp, int which, double *ref) {
   CK(cudaSetDevice(c->device));
@@ -3143,8 +3161,7 @@ void mgpu_gp_set_vars(mgpu_ctx *c, int gp, int which, const double *ref) {
   vars_ref_to_internal(c, ref, tmp);
   tmp.resize(c->var_len, 0.0);
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(which ? c->vars_k[gp] : c->vars_n[gp], tmp.data(), tmp.size() * sizeof(double),
-                cudaMemcpyHostToDevice));
+  h2d_sync(c, which ? c->vars_k[gp] : c->vars_n[gp], tmp.data(), tmp.size() * sizeof(double));
 }
 
 // ---- wave set-up ----------------------------------------------------------------------------
@@ -3176,18 +3193,17 @@ void mgpu_set_slot_strain(mgpu_ctx *c, int n, const int *slots, const double *ep
   bool contiguous = true;
   for (int i = 1; i < n; ++i) contiguous &= (slots[i] == slots[0] + i);
   if (contiguous && n > 0) {
-    CK(cudaMemcpy(c->T.eps + (size_t)slots[0] * 6, eps6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice));
+    h2d_sync(c, c->T.eps + (size_t)slots[0] * 6, eps6, sizeof(double) * 6 * n);
   } else {
     for (int i = 0; i < n; ++i)
-      CK(cudaMemcpy(c->T.eps + (size_t)slots[i] * 6, eps6 + (size_t)i * 6, sizeof(double) * 6,
-                    cudaMemcpyHostToDevice));
+      h2d_sync(c, c->T.eps + (size_t)slots[i] * 6, eps6 + (size_t)i * 6, sizeof(double) * 6);
   }
 }
 
 void mgpu_set_list(mgpu_ctx *c, int which_list, int n, const int *slots) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(c->d_list[which_list], slots, sizeof(int) * n, cudaMemcpyHostToDevice));
+  h2d_sync(c, c->d_list[which_list], slots, sizeof(int) * n);
 }
 
 // ---- kernels --------------------------------------------------------------------------------
@@ -3311,9 +3327,9 @@ static void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
       const long want_blocks = 148L * 4 * 2;
       rs = (int)std::max(1L, std::min((long)rs, (long)n * t2.ntiles / want_blocks));
       ntl = 1;
-      if (n < 4) {
+      if (n < 4) {  // one (or a few) large RVEs, e.g. a z-slab: several tiles per block, but at least ~4 waves of blocks
         rs = n;
-        ntl = TMA_MAX_RS / rs;
+        ntl = (int)std::max(1L, std::min((long)(TMA_MAX_RS / rs), (long)n * t2.ntiles / (148L * 4 * 4)));
       }
       const dim3 grid((t2.ntiles + ntl - 1) / ntl, (n + rs - 1) / rs);
       const int smem = kTmac[variant - 1].nstage * ((c->tile2_smem + 127) / 128 * 128) + 128;
@@ -3577,6 +3593,7 @@ void *mgpu_slab_mail(mgpu_ctx *c) {
   if (!c->slab_mail) {
     CK(cudaMalloc(&c->slab_mail, sizeof(SlabMail)));
     CK(cudaMemset(c->slab_mail, 0, sizeof(SlabMail)));
+    CK(cudaDeviceSynchronize());
   }
   return c->slab_mail;
 }
@@ -3614,11 +3631,10 @@ void mgpu_slab_link(mgpu_ctx *c, int rank, int size, void *const *mails, const v
   c->slab_lo_npad = lo_npad;
   c->slab_hi_off = hi_off;
   c->slab_hi_npad = hi_npad;
-  c->slab_ep_p = c->slab_ep_red = 0;
 }
 void mgpu_slab_publish_p(mgpu_ctx *c) {
   c->launches++;
-  k_slab_publish_p<<<1, 1, 0, c->stream>>>(c->slab_mail, ++c->slab_ep_p);
+  k_slab_publish_p<<<1, 1, 0, c->stream>>>(c->slab_mail);
   CK(cudaGetLastError());
 }
 void mgpu_slab_halo_pull(mgpu_ctx *c) {
@@ -3627,18 +3643,18 @@ void mgpu_slab_halo_pull(mgpu_ctx *c) {
   k_slab_halo_pull<<<dim3(nb, 2), NT, 0, c->stream>>>(
       c->mc, c->V.p, c->slab_mail, c->slab_p_lo, c->slab_lo_off, c->slab_lo_npad,
       c->slab_rank > 0 ? c->slab_peers.mail[c->slab_rank - 1] : nullptr, c->slab_p_hi, c->slab_hi_off, c->slab_hi_npad,
-      c->slab_rank + 1 < c->slab_size ? c->slab_peers.mail[c->slab_rank + 1] : nullptr, c->slab_ep_p);
+      c->slab_rank + 1 < c->slab_size ? c->slab_peers.mail[c->slab_rank + 1] : nullptr);
   CK(cudaGetLastError());
 }
 void mgpu_slab_post(mgpu_ctx *c, int k) {
   c->launches++;
-  k_slab_post<<<1, 32, 0, c->stream>>>(c->T.red, c->slab_mail, k, ++c->slab_ep_red);
+  k_slab_post<<<1, 32, 0, c->stream>>>(c->T.red, c->slab_mail, k);
   CK(cudaGetLastError());
 }
 void mgpu_slab_gather_tail(mgpu_ctx *c, int l, int k, int kind, int mode) {
   c->launches++;
   k_slab_gather_tail<<<dim3(1, 1), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
-                                                      c->slab_size, k, c->slab_ep_red, kind, mode);
+                                                      c->slab_size, k, kind, mode);
   CK(cudaGetLastError());
 }
 int mgpu_slab_error(mgpu_ctx *c) {
@@ -3660,6 +3676,32 @@ void mgpu_slab_cg_iteration(mgpu_ctx *c, int l, int op) {
   mgpu_slab_gather_tail(c, l, 2, 3, 0);
   mgpu_cg_pupdate(c, l, 1);
   mgpu_slab_publish_p(c);
+}
+// `iters` DPCG iterations of this rank's slab as ONE CUDA graph launch (captured once per (op, iters); the epochs of
+// the cross-rank flags live on the device, so every kernel argument is constant).  Slots that converge inside the
+// chunk skip their kernels (cg_active), exactly as in the single-domain chunked loop.
+void mgpu_slab_cg_chunk(mgpu_ctx *c, int l, int op, int iters) {
+  CK(cudaSetDevice(c->device));
+  const int key = op * 1024 + iters;
+  auto it = c->slab_chunk_graphs.find(key);
+  if (it == c->slab_chunk_graphs.end()) {
+    const bool prof = c->prof;
+    c->prof = false;
+    const unsigned long long l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    for (int k = 0; k < iters; ++k) mgpu_slab_cg_iteration(c, l, op);
+    CK(cudaStreamEndCapture(c->stream, &g));
+    cudaGraphExec_t ex = nullptr;
+    CK(cudaGraphInstantiate(&ex, g, 0));
+    CK(cudaGraphDestroy(g));
+    c->slab_launches_per_chunk = (int)(c->launches - l0);
+    c->launches = l0;
+    c->prof = prof;
+    it = c->slab_chunk_graphs.emplace(key, ex).first;
+  }
+  CK(cudaGraphLaunch(it->second, c->stream));
+  c->launches += c->slab_launches_per_chunk;
 }
 }
 
@@ -3696,8 +3738,7 @@ void mgpu_stage_put_vec(mgpu_ctx *c, int slot, int which, const double *host_aos
   std::vector<double> tmp;
   aos_to_soa(c, host_aos, tmp);
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(vec_of(c, which) + (size_t)slot * c->V.vstride, tmp.data(), tmp.size() * sizeof(double),
-                cudaMemcpyHostToDevice));
+  h2d_sync(c, vec_of(c, which) + (size_t)slot * c->V.vstride, tmp.data(), tmp.size() * sizeof(double));
 }
 void mgpu_stage_get_vec(mgpu_ctx *c, int slot, int which, double *host_aos) {
   CK(cudaSetDevice(c->device));
@@ -3720,7 +3761,7 @@ void mgpu_stage_put_vars(mgpu_ctx *c, int slot, int which, const double *ref) {
     std::vector<double> tmp;
     vars_ref_to_internal(c, ref, tmp);
     tmp.resize(c->var_len, 0.0);
-    CK(cudaMemcpy(bufs[slot], tmp.data(), sizeof(double) * c->var_len, cudaMemcpyHostToDevice));
+    h2d_sync(c, bufs[slot], tmp.data(), sizeof(double) * c->var_len);
   }
   if (which == 0)
     c->h_vars_old[slot] = ref ? bufs[slot] : nullptr;
@@ -3768,7 +3809,7 @@ void mgpu_stage_put_mat(mgpu_ctx *c, int slot, const double *vals) {
   CK(cudaStreamSynchronize(c->stream));
   const size_t len = (size_t)c->mc.nn * 3 * 81;
   if (!c->V.gen) CK(cudaMalloc(&c->V.gen, sizeof(double) * len));
-  CK(cudaMemcpy(c->V.gen, vals, sizeof(double) * len, cudaMemcpyHostToDevice));
+  h2d_sync(c, c->V.gen, vals, sizeof(double) * len);
 }
 
 void mgpu_ell_cols(int nx, int ny, int nz, int *cols, int device) {

@@ -99,6 +99,7 @@ def _bind(lib):
         "mgpu_slab_publish_p": (None, [V]), "mgpu_slab_halo_pull": (None, [V]), "mgpu_slab_post": (None, [V, C.c_int]),
         "mgpu_slab_gather_tail": (None, [V, C.c_int, C.c_int, C.c_int, C.c_int]),
         "mgpu_slab_error": (C.c_int, [V]), "mgpu_slab_cg_iteration": (None, [V, C.c_int, C.c_int]),
+        "mgpu_slab_cg_chunk": (None, [V, C.c_int, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -310,13 +311,14 @@ class SlabRVE:
         if peer:
             self._each(lib.mgpu_slab_publish_p)
         while self.slabs[0].state().cg_active:
+            if peer and self.world is not None:
+                # one CUDA graph launch per chunk of iterations, nothing but kernels: the cross-rank steps (halo pull,
+                # rank-ordered sums) are device-side, their epochs live in the mailboxes
+                self.exchanges += self.cg_chunk
+                self.allreduces += 2 * self.cg_chunk
+                lib.mgpu_slab_cg_chunk(self.slabs[0].ctx, L0, self.op, self.cg_chunk)
+                continue
             for _ in range(self.cg_chunk):
-                if peer and self.world is not None:
-                    # one call per iteration, nothing but kernel launches: the cross-rank steps are device-side
-                    self.exchanges += 1
-                    self.allreduces += 2
-                    lib.mgpu_slab_cg_iteration(self.slabs[0].ctx, L0, self.op)
-                    continue
                 self._exchange_p()
                 self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, self.op), 1, 2)
                 self._reduced(lib.mgpu_cg_update, (L0, 1), 2, 3)
