@@ -1162,6 +1162,26 @@ __device__ __forceinline__ double fold_partials(const double *partial, int n) {
   return acc;
 }
 
+// z.z and r.z of k_cg_update / k_cg_update_imp: one warp per slot folds the per-block partials (planes 0 and 1) in a
+// fixed order, then the scalar tail of the iteration and the loop-head test of the next one (src/ell.cpp:108-119)
+__global__ void k_fold_update(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, int nblk) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!st->cg_active) return;
+  const double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  const double zz = fold_partials(partial, nblk);
+  const double rz = fold_partials(partial + T.nblk_max, nblk);
+  if (threadIdx.x == 0) {
+    if (P.slab) {
+      T.red[slot * 8] = zz;
+      T.red[slot * 8 + 1] = rz;
+    } else {
+      tail_cg_update(P, st, zz, rz);
+    }
+  }
+}
+
 // slab mode / forced applications: fold p.Ap right after the SpMV (one warp per slot)
 __global__ void k_fold_spmv(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, int nfold, int force) {
   const int slot = slot_of(L);
@@ -1725,8 +1745,7 @@ __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, i
 __global__ void __launch_bounds__(NT, 4)
     k_cg_update_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int nfold) {
   __shared__ double sm[NRED * (NT / 32)];
-  __shared__ int sflag;
-  __shared__ double s_alpha;
+    __shared__ double s_alpha;
   const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
@@ -1790,14 +1809,13 @@ __global__ void __launch_bounds__(NT, 4)
       }
     }
   }
-  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
-  if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    if (P.slab) {
-      T.red[slot * 8] = red[0];
-      T.red[slot * 8 + 1] = red[1];
-    } else {
-      tail_cg_update(P, st, red[0], red[1]);
-    }
+  // per-block partial sums only: no ticket, no fence -- k_fold_update (one warp per slot) folds them in a fixed order
+  // and runs the scalar tail; the kernel boundary orders it after these stores
+  block_sum<2>(red, sm);
+  if (threadIdx.x == 0) {
+    double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+    partial[blockIdx.x] = red[0];
+    partial[T.nblk_max + blockIdx.x] = red[1];
   }
 }
 
@@ -1869,8 +1887,7 @@ __global__ void __launch_bounds__(NT)
 __global__ void __launch_bounds__(NT, 4)
     k_cg_update(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
   __shared__ double sm[NRED * (NT / 32)];
-  __shared__ int sflag;
-  const int slot = slot_of(L);
+    const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!st->cg_active) return;
@@ -1907,14 +1924,13 @@ __global__ void __launch_bounds__(NT, 4)
       }
     }
   }
-  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
-  if (grid_sum<2>(red, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) {
-    if (P.slab) {
-      T.red[slot * 8] = red[0];
-      T.red[slot * 8 + 1] = red[1];
-    } else {
-      tail_cg_update(P, st, red[0], red[1]);
-    }
+  // per-block partial sums only: no ticket, no fence -- k_fold_update (one warp per slot) folds them in a fixed order
+  // and runs the scalar tail; the kernel boundary orders it after these stores
+  block_sum<2>(red, sm);
+  if (threadIdx.x == 0) {
+    double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+    partial[blockIdx.x] = red[0];
+    partial[T.nblk_max + blockIdx.x] = red[1];
   }
 }
 
@@ -3388,6 +3404,8 @@ void mgpu_cg_update(mgpu_ctx *c, int l, int n) {
     k_cg_update_imp<<<upd_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, imp_fold_count(c));
   else
     k_cg_update<<<upd_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  k_fold_update<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, (int)upd_grid(c, n).x);
+  c->launches++;
   CK(cudaGetLastError());
 }
 void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
