@@ -110,6 +110,9 @@ void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_share
 /* use_shared selects the operator of the solve: 0 the slot's own matrix, 1 the shared A0, 2 the generic host matrix,
    3 the implicit operator of an all-elastic RVE (mgpu_implicit() != 0); mgpu_cg_update/pupdate follow the operator
    of the last mgpu_cg_init */
+/* host-only (no GPU): tiling of the implicit operator's TMA kernel for an nx x ny x nz RVE; see mgpu_kernels.cu */
+int mgpu_tmac_tiling_host(int nx, int ny, int nz, const int *elem_type, int *meta6, int *rowid, int *tiles4,
+                          int *chunk_pure, int *fix_ptr, int *tasks4);
 int mgpu_implicit(const mgpu_ctx *);
 int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
 int mgpu_implicit_fix_nodes(const mgpu_ctx *); /* interior nodes on material interfaces (fix-up list of the TMA kernel) */

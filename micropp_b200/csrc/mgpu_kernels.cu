@@ -2594,9 +2594,155 @@ double *vec_of(mgpu_ctx *c, int which) {
   }
 }
 
+// ---- pure host helpers of the implicit operator (no CUDA calls: also reachable from the CPU tests) ----
+// Row-block id of every interior node: code = sum_c type_c 3^c over the 8 elements around the node (c as in
+// k_asm_mat_elastic); ids 0..2 are reserved for nodes whose 8 elements are all of material 0 / 1 / 2.
+static void implicit_row_ids(int nix, int niy, int niz, int nint_pad, const int *elem_type, std::vector<int> &codes,
+                             std::vector<int> &rowid) {
+  const int nex = nix + 1, ney = niy + 1;
+  std::vector<int> code2id(6561, -1);
+  codes.clear();
+  rowid.assign(std::max(nint_pad, nix * niy * niz), 0);
+  for (int t = 0; t < 3; ++t) {
+    code2id[t * 3280] = t;
+    codes.push_back(t * 3280);
+  }
+  const int nint = nix * niy * niz;
+  for (int m = 0; m < nint; ++m) {
+    const int pl = nix * niy;
+    const int kk = m / pl, r = m - kk * pl, jj = r / nix, ii = r - jj * nix;
+    const int i = ii + 1, j = jj + 1, k = kk + 1;
+    int code = 0, w3 = 1;
+    for (int cc = 0; cc < 8; ++cc) {
+      const int ex = i - 1 + ((cc >> 2) & 1), ey = j - 1 + ((cc >> 1) & 1), ez = k - 1 + (cc & 1);
+      code += w3 * elem_type[(ez * ney + ey) * nex + ex];
+      w3 *= 3;
+    }
+    if (code2id[code] < 0) {
+      code2id[code] = (int)codes.size();
+      codes.push_back(code);
+    }
+    rowid[m] = code2id[code];
+  }
+}
+
+// Tiling of k_spmv_dot_tmac: nodes per thread (7 or 8), warps per block, tile descriptors (two lane shapes), the pure
+// row block + fix-up mask of every chunk, and the fix-up tasks of every tile.
+struct TmacTiling {
+  int tn = 8, cb = 1, nchunk = 0, pitch = 0;
+  std::vector<int4> tiles, tasks;
+  std::vector<int> chunk_pure, fix_ptr;
+};
+static TmacTiling tmac_tiling(int nix, int niy, int niz, const std::vector<int> &rowid) {
+  TmacTiling t2;
+  long best = -1;
+  for (int tn = 8; tn >= 7; --tn)
+    for (int cb = 4; cb >= 1; --cb) {
+      const int nch = (nix + tn - 1) / tn;
+      if (cb > nch) continue;
+      const long exec = (long)((nch + cb - 1) / cb) * cb * tn;  // executed node slots per x row
+      // fewer executed slots; blocks of 1 or 2 warps pay for their relatively larger halo and overheads
+      const long score = exec * (cb >= 3 ? 100 : cb == 2 ? 115 : 140) + (4 - cb);
+      if (best < 0 || score < best) {
+        best = score;
+        t2.tn = tn;
+        t2.cb = cb;
+      }
+    }
+  const int TN = t2.tn;
+  t2.nchunk = (nix + TN - 1) / TN;
+  t2.pitch = tmac_pitch(TN, t2.cb);
+  // y is covered by 8-row tiles of lane shape 0; a remainder of 1..4 rows becomes a strip of shape-1 tiles
+  const int yrem = niy % TILE_Y, y_a = (yrem >= 1 && yrem <= 4) ? niy - yrem : niy;
+  std::vector<int4> &tiles = t2.tiles;
+  const int tiles_x = (t2.nchunk + t2.cb - 1) / t2.cb;
+  for (int z0 = 0; z0 < niz; z0 += TILE_Z)
+    for (int y0 = 0; y0 < y_a; y0 += TILE_Y)
+      for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y0, z0, 0));
+  if (y_a < niy)
+    for (int z0 = 0; z0 < niz; z0 += TILE_Y)
+      for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y_a, z0, 1));
+  const int ntiles = (int)tiles.size();
+  std::vector<int> &chunk_pure = t2.chunk_pure, &fix_ptr = t2.fix_ptr;
+  chunk_pure.assign((size_t)niz * niy * t2.nchunk, 0);
+  fix_ptr.assign(ntiles + 1, 0);
+  std::vector<int4> &tasks = t2.tasks;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int4 td = tiles[tile];
+    std::vector<int2> fix;
+    fix_ptr[tile] = (int)tasks.size();
+    const int ny_t = td.w ? TILE_Z : TILE_Y, nz_t = td.w ? TILE_Y : TILE_Z;
+    for (int rz = 0; rz < nz_t; ++rz)
+      for (int ry = 0; ry < ny_t; ++ry)
+        for (int wq = 0; wq < t2.cb; ++wq) {
+          const int kk = td.z + rz, jj = td.y + ry, cc = td.x + wq;
+          if (kk >= niz || jj >= niy || cc >= t2.nchunk) continue;
+          const int m0 = (kk * niy + jj) * nix + cc * TN, nv = std::min(TN, nix - cc * TN);
+          int cnt[3] = {0, 0, 0};
+          for (int t = 0; t < nv; ++t)
+            if (rowid[m0 + t] < 3) cnt[rowid[m0 + t]]++;
+          int pure = 0;
+          for (int q = 1; q < 3; ++q)
+            if (cnt[q] > cnt[pure]) pure = q;
+          int mask = 0;
+          for (int t = 0; t < nv; ++t)
+            if (rowid[m0 + t] != pure) {
+              mask |= 1 << t;
+              int2 e;
+              e.x = (wq * TN + t) | (ry << 8) | (rz << 12);
+              e.y = rowid[m0 + t];
+              fix.push_back(e);
+            }
+          chunk_pure[((size_t)kk * niy + jj) * t2.nchunk + cc] = pure | (mask << 8);
+        }
+    // lanes of a warp take consecutive entries: sorted by row-block id, neighbouring lanes fetch the same
+    // row block (the loads of a fix-up round are bound by the distinct 32-B sectors a warp touches)
+    std::stable_sort(fix.begin(), fix.end(), [](const int2 &a, const int2 &b) { return a.y < b.y; });
+    // tasks: two nodes with the same row block share one task (one set of row-block loads)
+    for (size_t q = 0; q < fix.size();) {
+      if (q + 1 < fix.size() && fix[q + 1].y == fix[q].y) {
+        tasks.push_back(make_int4(fix[q].x, fix[q + 1].x, fix[q].y, 0));
+        q += 2;
+      } else {
+        tasks.push_back(make_int4(fix[q].x, -1, fix[q].y, 0));
+        q += 1;
+      }
+    }
+  }
+  fix_ptr[ntiles] = (int)tasks.size();
+  return t2;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Host-only view of the implicit operator's tiling for an nx x ny x nz RVE (tests/test_tiling.py, no GPU needed).
+// meta[6] = {nodes per thread, warps per block, chunks per x row, brick pitch, tiles, fix-up tasks}; the arrays may be
+// null (size query): rowid[(nx-2)(ny-2)(nz-2)], tiles[4 * ntiles], chunk_pure[niz * niy * nchunk], fix_ptr[ntiles + 1],
+// tasks[4 * ntasks].  Returns the number of distinct row blocks.
+int mgpu_tmac_tiling_host(int nx, int ny, int nz, const int *elem_type, int *meta, int *rowid_out, int *tiles,
+                          int *chunk_pure, int *fix_ptr, int *tasks) {
+  const int nix = nx - 2, niy = ny - 2, niz = nz - 2;
+  if (nix < 1 || niy < 1 || niz < 1) return 0;
+  std::vector<int> codes, rowid;
+  implicit_row_ids(nix, niy, niz, nix * niy * niz, elem_type, codes, rowid);
+  const TmacTiling t = tmac_tiling(nix, niy, niz, rowid);
+  if (meta) {
+    meta[0] = t.tn;
+    meta[1] = t.cb;
+    meta[2] = t.nchunk;
+    meta[3] = t.pitch;
+    meta[4] = (int)t.tiles.size();
+    meta[5] = (int)t.tasks.size();
+  }
+  if (rowid_out) memcpy(rowid_out, rowid.data(), sizeof(int) * (size_t)nix * niy * niz);
+  if (tiles) memcpy(tiles, t.tiles.data(), sizeof(int4) * t.tiles.size());
+  if (chunk_pure) memcpy(chunk_pure, t.chunk_pure.data(), sizeof(int) * t.chunk_pure.size());
+  if (fix_ptr) memcpy(fix_ptr, t.fix_ptr.data(), sizeof(int) * t.fix_ptr.size());
+  if (tasks && !t.tasks.empty()) memcpy(tasks, t.tasks.data(), sizeof(int4) * t.tasks.size());
+  return (int)codes.size();
+}
 
 int mgpu_device_count(void) {
   int n = 0;
@@ -2772,27 +2918,8 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
 
   if (c->implicit) {
     // distinct row blocks: code = sum_c type_c 3^c over the 8 elements around an interior node
-    std::vector<int> code2id(6561, -1), codes, rowid(P.nint_pad, 0);
-    for (int t = 0; t < 3; ++t) {  // ids 0..2: nodes whose 8 elements are all of material t (kept in shared memory)
-      code2id[t * 3280] = t;
-      codes.push_back(t * 3280);
-    }
-    for (int m = 0; m < P.nint; ++m) {
-      const int pl = P.nix * P.niy;
-      const int kk = m / pl, r = m - kk * pl, jj = r / P.nix, ii = r - jj * P.nix;
-      const int i = ii + 1, j = jj + 1, k = kk + 1;
-      int code = 0, w3 = 1;
-      for (int cc = 0; cc < 8; ++cc) {
-        const int ex = i - 1 + ((cc >> 2) & 1), ey = j - 1 + ((cc >> 1) & 1), ez = k - 1 + (cc & 1);
-        code += w3 * cfg->elem_type[(ez * P.ney + ey) * P.nex + ex];
-        w3 *= 3;
-      }
-      if (code2id[code] < 0) {
-        code2id[code] = (int)codes.size();
-        codes.push_back(code);
-      }
-      rowid[m] = code2id[code];
-    }
+    std::vector<int> codes, rowid;
+    implicit_row_ids(P.nix, P.niy, P.niz, P.nint_pad, cfg->elem_type, codes, rowid);
     c->nrows = (int)codes.size();
     int *d_codes = nullptr, *d_rowid = nullptr;
     double *d_rows = nullptr, *d_rkinv = nullptr;
@@ -2917,80 +3044,16 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
           // ---- tiling of k_spmv_dot_tmac: TN nodes per thread, cb warps per block, tile descriptors ----
           {
             TileInfo2 &t2 = c->tile2;
-            long best = -1;
-            for (int tn = 8; tn >= 7; --tn)
-              for (int cb = 4; cb >= 1; --cb) {
-                const int nch = (P.nix + tn - 1) / tn;
-                if (cb > nch) continue;
-                const long exec = (long)((nch + cb - 1) / cb) * cb * tn;  // executed node slots per x row
-                // fewer executed slots; blocks of 1 or 2 warps pay for their relatively larger halo and overheads
-                const long score = exec * (cb >= 3 ? 100 : cb == 2 ? 115 : 140) + (4 - cb);
-                if (best < 0 || score < best) {
-                  best = score;
-                  t2.tn = tn;
-                  t2.cb = cb;
-                }
-              }
+            TmacTiling tt = tmac_tiling(P.nix, P.niy, P.niz, rowid);
+            t2.tn = tt.tn;
+            t2.cb = tt.cb;
+            t2.nchunk = tt.nchunk;
+            t2.pitch = tt.pitch;
+            t2.ntiles = (int)tt.tiles.size();
             const int TN = t2.tn;
-            t2.nchunk = (P.nix + TN - 1) / TN;
-            t2.pitch = tmac_pitch(TN, t2.cb);
             c->tile2_smem = (int)(sizeof(double) * 3 * BRICK_ROWS * t2.pitch);
-            // y is covered by 8-row tiles of lane shape 0; a remainder of 1..4 rows becomes a strip of shape-1 tiles
-            const int yrem = P.niy % TILE_Y, y_a = (yrem >= 1 && yrem <= 4) ? P.niy - yrem : P.niy;
-            std::vector<int4> tiles;
-            const int tiles_x = (t2.nchunk + t2.cb - 1) / t2.cb;
-            for (int z0 = 0; z0 < P.niz; z0 += TILE_Z)
-              for (int y0 = 0; y0 < y_a; y0 += TILE_Y)
-                for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y0, z0, 0));
-            if (y_a < P.niy)
-              for (int z0 = 0; z0 < P.niz; z0 += TILE_Y)
-                for (int tx = 0; tx < tiles_x; ++tx) tiles.push_back(make_int4(tx * t2.cb, y_a, z0, 1));
-            t2.ntiles = (int)tiles.size();
-            std::vector<int> chunk_pure((size_t)P.niz * P.niy * t2.nchunk, 0), fix_ptr(t2.ntiles + 1, 0);
-            std::vector<int4> tasks;
-            for (int tile = 0; tile < t2.ntiles; ++tile) {
-              const int4 td = tiles[tile];
-              std::vector<int2> fix;
-              fix_ptr[tile] = (int)tasks.size();
-              const int ny_t = td.w ? TILE_Z : TILE_Y, nz_t = td.w ? TILE_Y : TILE_Z;
-              for (int rz = 0; rz < nz_t; ++rz)
-                for (int ry = 0; ry < ny_t; ++ry)
-                  for (int wq = 0; wq < t2.cb; ++wq) {
-                    const int kk = td.z + rz, jj = td.y + ry, cc = td.x + wq;
-                    if (kk >= P.niz || jj >= P.niy || cc >= t2.nchunk) continue;
-                    const int m0 = (kk * P.niy + jj) * P.nix + cc * TN, nv = std::min(TN, P.nix - cc * TN);
-                    int cnt[3] = {0, 0, 0};
-                    for (int t = 0; t < nv; ++t)
-                      if (rowid[m0 + t] < 3) cnt[rowid[m0 + t]]++;
-                    int pure = 0;
-                    for (int q = 1; q < 3; ++q)
-                      if (cnt[q] > cnt[pure]) pure = q;
-                    int mask = 0;
-                    for (int t = 0; t < nv; ++t)
-                      if (rowid[m0 + t] != pure) {
-                        mask |= 1 << t;
-                        int2 e;
-                        e.x = (wq * TN + t) | (ry << 8) | (rz << 12);
-                        e.y = rowid[m0 + t];
-                        fix.push_back(e);
-                      }
-                    chunk_pure[((size_t)kk * P.niy + jj) * t2.nchunk + cc] = pure | (mask << 8);
-                  }
-              // lanes of a warp take consecutive entries: sorted by row-block id, neighbouring lanes fetch the same
-              // row block (the loads of a fix-up round are bound by the distinct 32-B sectors a warp touches)
-              std::stable_sort(fix.begin(), fix.end(), [](const int2 &a, const int2 &b) { return a.y < b.y; });
-              // tasks: two nodes with the same row block share one task (one set of row-block loads)
-              for (size_t q = 0; q < fix.size();) {
-                if (q + 1 < fix.size() && fix[q + 1].y == fix[q].y) {
-                  tasks.push_back(make_int4(fix[q].x, fix[q + 1].x, fix[q].y, 0));
-                  q += 2;
-                } else {
-                  tasks.push_back(make_int4(fix[q].x, -1, fix[q].y, 0));
-                  q += 1;
-                }
-              }
-            }
-            fix_ptr[t2.ntiles] = (int)tasks.size();
+            const std::vector<int4> &tiles = tt.tiles, &tasks = tt.tasks;
+            const std::vector<int> &chunk_pure = tt.chunk_pure, &fix_ptr = tt.fix_ptr;
             CK(cudaMalloc(&c->d_tiles2, sizeof(int4) * tiles.size()));
             h2d_sync(c, c->d_tiles2, tiles.data(), sizeof(int4) * tiles.size());
             CK(cudaMalloc(&c->d_chunk_pure2, sizeof(int) * chunk_pure.size()));
