@@ -14,6 +14,16 @@
 // Assembly is a *gather by node* instead of the reference's element scatter: each ELL value is
 // written exactly once, coalesced, with the element contributions added in the reference's element
 // visiting order -- no atomics, no colours, no read-modify-write traffic.
+//
+// Map of the file (DESIGN.md section 5 has bytes, bounds and measurements of every kernel):
+//   k_set_bc, k_elem_rhs + k_asm_rhs        boundary displacements, residual (per-element + node gather)
+//   k_asm_mat_elastic, k_elem_ctan + k_asm_mat_general, k_rows_build     Jacobian (assembled) / row-block table
+//   k_cg_init, k_spmv_dot, k_cg_update + k_fold_update, k_cg_pupdate, k_cg_finish      DPCG, assembled operator
+//   k_spmv_dot_tmac (+ _tma, _tile, _imp), k_fold_spmv, k_cg_update_imp, k_cg_pupdate_imp   DPCG, implicit operator
+//                                           of all-elastic RVEs (no per-RVE matrix; TMA-tiled, FP64-pipe-bound)
+//   k_axpy_u, k_ave_stress, k_vars_new, k_elem_fields, k_compact        Newton update, averages, history, lists
+//   k_slab_*                                z-slab mode of one large RVE over NVLink peer memory
+//   mgpu_*                                  the C ABI; mgpu_newton_step_graph = one Newton step as one CUDA graph
 #include <cuda.h>  // CUtensorMap (type + enums only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
