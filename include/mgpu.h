@@ -88,6 +88,7 @@ unsigned long long mgpu_launch_count(const mgpu_ctx *);
 void mgpu_gp_swap(mgpu_ctx *, int gp);              /* update_vars: pointer swaps (include/gp.hpp:95-105) */
 int mgpu_gp_has_vars(const mgpu_ctx *, int gp);
 void mgpu_gp_alloc_vars(mgpu_ctx *, int gp);        /* gp_t::allocate (include/gp.hpp:86-93): zeroed */
+void mgpu_gp_free_vars(mgpu_ctx *, int gp);         /* back to "no history" (buffers return to the pool) */
 /* reference-layout (AoS) import/export of u_n/u_k (which: 0=n,1=k) and vars_n/vars_k */
 void mgpu_gp_get_u(mgpu_ctx *, int gp, int which, double *host_aos);
 void mgpu_gp_set_u(mgpu_ctx *, int gp, int which, const double *host_aos);

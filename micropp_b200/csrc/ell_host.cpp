@@ -254,18 +254,22 @@ EllDev *ell_device(const int n[3], int max_its, double min_err, double rel_err) 
   return d;
 }
 
-void require_3d(const ell_matrix *m, const char *who) {
-  if (m->dim != 3 || m->nfield != 3) {
-    fprintf(stderr, "micropp-b200: %s is provided for the 3-D, 3-field ELL of the hot path only (dim=%d nfield=%d)\n",
-            who, m->dim, m->nfield);
-    abort();
-  }
-}
+// matrices of the hot path: 3-D grid, 3 fields (the batched kernels of homogenize()); everything else -- the 2-D and
+// other field counts of the reference's ELL API (test/test_ell_1.cpp) -- goes to the one-block kernels of
+// ell_generic.cu, which follow the explicit column table
+inline bool hot_path_shape(const ell_matrix *m) { return m->dim == 3 && m->nfield == 3; }
 
 }  // namespace
 
+extern "C" void mgpu_ell_generic_mvp(int nrow, int nnz, const int *cols, const double *vals, const double *x, double *y);
+extern "C" int mgpu_ell_generic_cg(int nrow, int nnz, int nfield, int shift, const int *cols, const double *vals,
+                                   const double *b, double *x, int max_its, double min_err, double rel_err, double *err);
+
 void ell_mvp(const ell_matrix *m, const double *x, double *y) {
-  require_3d(m, "ell_mvp");
+  if (!hot_path_shape(m)) {
+    mgpu_ell_generic_mvp(m->nrow, m->nnz, m->cols, m->vals, x, y);
+    return;
+  }
   EllDev *d = ell_device(m->n, m->max_its > 0 ? m->max_its : CG_MAX_ITS, m->min_err > 0 ? m->min_err : CG_ABS_TOL,
                          m->rel_err);
   const int s0 = 0;
@@ -279,7 +283,9 @@ void ell_mvp(const ell_matrix *m, const double *x, double *y) {
 
 int ell_solve_cgpd(const ell_matrix *m, const double *b, double *x, double *err) {
   if (!m || !b || !x) return 1;
-  require_3d(m, "ell_solve_cgpd");
+  if (!hot_path_shape(m))
+    return mgpu_ell_generic_cg(m->nrow, m->nnz, m->nfield, m->shift, m->cols, m->vals, b, x, m->max_its, m->min_err,
+                               m->rel_err, err);
   EllDev *d = ell_device(m->n, m->max_its, m->min_err, m->rel_err);
   const int s0 = 0;
   mgpu_ctx *ctx = d->eng.ctx;

@@ -3217,6 +3217,14 @@ void mgpu_gp_alloc_vars(mgpu_ctx *c, int gp) {
   c->vars_n[gp] = vars_buffer_alloc(c);
   c->vars_k[gp] = vars_buffer_alloc(c);
 }
+void mgpu_gp_free_vars(mgpu_ctx *c, int gp) {
+  if (!c->vars_n[gp]) return;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->var_free.push_back(c->vars_n[gp]);
+  c->var_free.push_back(c->vars_k[gp]);
+  c->vars_n[gp] = c->vars_k[gp] = nullptr;
+}
 void mgpu_gp_get_u(mgpu_ctx *c, int gp, int which, double *host_aos) {
   CK(cudaSetDevice(c->device));
   std::vector<double> tmp((size_t)3 * c->mc.nn_pad);
@@ -3449,8 +3457,19 @@ int mgpu_implicit_kernel(const mgpu_ctx *c) {
   return (k == 2 && c->tma_variant >= 1 && c->tile2.ntiles > 0) ? 3 : k;  // 3: k_spmv_dot_tmac
 }
 
+// OP_SLOT indexes the explicit matrix pool by slot: a context that serves all-elastic RVEs from the implicit operator
+// keeps only mat_slots (<= 2) explicit matrices for the host-pointer API, so a wider OP_SLOT launch would read past it
+static void require_mat_pool(const mgpu_ctx *c, int n, int op, const char *who) {
+  if (op == OP_SLOT && n > c->mat_slots) {
+    fprintf(stderr, "micropp-b200: %s over %d slots with per-slot matrices, but the matrix pool holds %d "
+                    "(implicit operator)\n", who, n, c->mat_slots);
+    abort();
+  }
+}
+
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
+  require_mat_pool(c, n, use_shared, "mgpu_cg_init");
   if (use_shared == OP_IMPLICIT && !c->implicit) {
     fprintf(stderr, "micropp-b200: implicit operator requested for an RVE that is not all-elastic\n");
     abort();
@@ -3462,6 +3481,7 @@ void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
 }
 void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
+  require_mat_pool(c, n, use_shared, "mgpu_cg_spmv_dot");
   ProfScope ps(c, 0, n);
   if (use_shared == OP_IMPLICIT) {
     launch_imp_spmv(c, l, n, 0, c->imp_kernel);
@@ -3943,6 +3963,7 @@ void mgpu_apply_operator(mgpu_ctx *c, int l, int n, int op, int imp_kernel) {
   } else if (op == OP_GENERIC) {
     k_spmv_generic<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, 1);
   } else {
+    require_mat_pool(c, n, op, "mgpu_apply_operator");
     k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, op, 1);
   }
   CK(cudaGetLastError());
@@ -3969,7 +3990,7 @@ float mgpu_timer_stop(mgpu_ctx *c) {
 }
 float mgpu_bench_spmv(mgpu_ctx *c, int n, int iters) {
   CK(cudaSetDevice(c->device));
-  n = std::min(n, c->W);
+  n = std::min(n, std::min(c->W, c->mat_slots));  // slots that own an explicit matrix
   std::vector<int> ids(n);
   for (int i = 0; i < n; ++i) ids[i] = i;
   mgpu_set_list(c, 5, n, ids.data());

@@ -650,16 +650,32 @@ void micropp<3>::read_restart(const int restart_id) const {
   std::stringstream name;
   name << "micropp-restart-" << mpi_rank << "-" << restart_id << ".bin";
   ifstream file(name.str(), ios::in | ios::binary);
+  if (!file.good()) {
+    cerr << "micropp-b200: cannot open restart file " << name.str() << endl;
+    return;
+  }
   std::vector<double> vars(nvars), u(nndim);
   for (int igp = 0; igp < ngp; ++igp) {
     gp_t<3> &g = gp_list[igp];
-    file.read((char *)&g.allocated, sizeof(bool));
-    if (g.allocated && g.fe_index >= 0) {
+    bool allocated = false;
+    file.read((char *)&allocated, sizeof(bool));
+    if (allocated) {
+      // the payload is always consumed, whatever this Gauss point is here, so that later ones stay aligned
       file.read((char *)vars.data(), nvars * sizeof(double));
       file.read((char *)u.data(), nndim * sizeof(double));
+    }
+    if (!file.good()) {
+      cerr << "micropp-b200: restart file " << name.str() << " is truncated at Gauss point " << igp << endl;
+      return;
+    }
+    if (g.fe_index < 0) continue;  // no FE state on this Gauss point (FE_LINEAR / mixture rule)
+    if (allocated) {
       mgpu_gp_set_vars(engine->ctx, g.fe_index, 0, vars.data());
       mgpu_gp_set_u(engine->ctx, g.fe_index, 0, u.data());
+    } else if (g.allocated) {
+      mgpu_gp_free_vars(engine->ctx, g.fe_index);  // back to "no history": stale device buffers must not survive
     }
+    g.allocated = allocated;
   }
 }
 

@@ -46,39 +46,60 @@ def balanced_ranges(costs, nproc: int) -> list[tuple[int, int]]:
     `costs[g]` is what Gauss point g cost in the last macro step -- ``micropp<3>::get_cost`` (CG iterations,
     src/homogenize.cpp:127-131), what the reference's test/mpi-load-balance.cpp:56-73 shows to differ by 3-5x between
     linear and non-linear Gauss points.  Ranges stay contiguous (a macro code scatters strains by slice; the FE state
-    of a Gauss point lives on its GPU, so a re-shard moves `u_n`/`vars_n` through write_restart/read_restart).  With
-    equal costs the result is `gp_range` (remainders to the low ranks).  Exact: binary search on the bottleneck value
-    with a greedy feasibility sweep, O(ngp log(sum))."""
+    of a Gauss point lives on its GPU, so a re-shard moves `u_n`/`vars_n` through write_restart/read_restart).
+
+    Equal costs reproduce `gp_range` exactly (the reference drivers' rule, remainders to the low ranks).  Otherwise:
+    (1) the minimal bottleneck B by binary search with a greedy feasibility sweep, (2) a left-to-right pass that ends
+    rank r at the position closest to the cumulative target (r+1)/nproc of the total, subject to every part <= B and
+    to the rest still fitting the remaining ranks -- so the parts are even, not just bounded."""
     w = [max(float(c), 0.0) + 1.0 for c in costs]   # +1: a linear GP still costs its set-up, and empty ranks are avoided
     ngp = len(w)
     nproc = max(1, int(nproc))
     if ngp == 0:
         return [(0, 0)] * nproc
+    if max(w) == min(w):
+        return [gp_range(ngp, nproc, r) for r in range(nproc)]
 
-    def cuts(limit):
-        out, acc, begin = [], 0.0, 0
-        for g, c in enumerate(w):
-            if acc + c > limit and g > begin:
-                out.append((begin, g))
-                begin, acc = g, 0.0
-            acc += c
-        out.append((begin, ngp))
-        return out
+    def nparts(limit, begin):
+        """greedy count of parts of cost <= limit that cover [begin, ngp)"""
+        n, acc = 1, 0.0
+        for g in range(begin, ngp):
+            if acc + w[g] > limit and acc > 0.0:
+                n, acc = n + 1, 0.0
+            acc += w[g]
+        return n if begin < ngp else 0
 
     lo, hi = max(w), sum(w)
     for _ in range(60):
         mid = 0.5 * (lo + hi)
-        if len(cuts(mid)) <= nproc:
+        if nparts(mid, 0) <= nproc:
             hi = mid
         else:
             lo = mid
-    parts = cuts(hi)
-    # fewer parts than ranks: split the longest ranges so that every rank owns work when ngp >= nproc
-    while len(parts) < nproc:
-        k = max(range(len(parts)), key=lambda q: parts[q][1] - parts[q][0])
-        b, e = parts[k]
-        if e - b < 2:
-            break
-        parts[k:k + 1] = [(b, (b + e) // 2), ((b + e) // 2, e)]
-    parts += [(ngp, ngp)] * (nproc - len(parts))
+    B = hi * (1.0 + 1e-12)
+    total = sum(w)
+    pre = [0.0]
+    for c in w:
+        pre.append(pre[-1] + c)
+    parts, begin = [], 0
+    for r in range(nproc):
+        left = nproc - r - 1                      # ranks after this one
+        if r == nproc - 1 or begin >= ngp:
+            parts.append((begin, ngp if r == nproc - 1 else begin))
+            begin = parts[-1][1]
+            continue
+        target = total * (r + 1) / nproc
+        best, best_d = None, None
+        for end in range(begin + 1, ngp - left + 1 if ngp - begin > left else ngp + 1):
+            if pre[end] - pre[begin] > B:
+                break
+            if nparts(B, end) > left:
+                continue
+            d = abs(pre[end] - target)
+            if best is None or d < best_d:
+                best, best_d = end, d
+        if best is None:
+            best = min(begin + 1, ngp)
+        parts.append((begin, best))
+        begin = best
     return parts

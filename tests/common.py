@@ -16,6 +16,13 @@ CASES = {
                           materials=[EL(1e6), PL(1e3, 0.3, 5e4, 1e3), EL(1e6)]),
     "plastic_fibre": dict(type=4, geo_params=(0.2, 0.0, 0.0, 0.0),
                           materials=[EL(1e6), PL(1e3, 0.3, 5e4, 1e3), EL(1e6)]),
+    # the same micro-structures with the reference's golden plastic material (test/benchmark-plastic.cpp:78), the one
+    # bench.py's plastic40 workload uses: E = 3e7, Sy = 1e5 yields at strains of a few 1e-3, so the J2 return mapping,
+    # its forward-difference tangent and the state-variable update are really exercised (E = Sy = 1e3 above never yields)
+    "plastic_layer_yield": dict(type=2, geo_params=(0.5, 0.0, 0.0, 0.0),
+                                materials=[EL(3e7, 0.25), PL(3e7, 0.25, 1e7, 1e5), EL(3e7, 0.25)]),
+    "plastic_fibre_yield": dict(type=4, geo_params=(0.2, 0.0, 0.0, 0.0),
+                                materials=[EL(3e7, 0.25), PL(3e7, 0.25, 1e7, 1e5), EL(3e7, 0.25)]),
     "homog_damage": dict(type=0, materials=[DM(1e7, 0.3, 1e5), EL(1e7), EL(1e7)]),
     "mic3d_8": dict(type=10, materials=[EL(1e7), EL(1e8), DM(5e6, 0.3, 1e5)]),
 }

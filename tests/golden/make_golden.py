@@ -60,7 +60,12 @@ def stage_fixture(case, dims, seed):
     out.update(nr_eps=e3, nr_u=un, nr_its=st["its"], nr_solver_its=st["solver_its"], nr_conv=st["converged"],
                nr_sig=r.ave_stress(un))
     r.close()
+    if case in MUST_BE_NON_LINEAR:
+        assert out["nl_v"] and out["nl_nov"], f"{case}: the stage fixture must exercise the non-linear material branch"
     return out
+
+
+MUST_BE_NON_LINEAR = ("damage_sphere", "plastic_layer_yield", "mic3d_8")
 
 
 def history_fixture(case, n, ngp, steps, seed, comp, nr_max_its, eps_max=0.1, dt=0.015, reverse_after=None, inc=None):
@@ -90,6 +95,8 @@ def history_fixture(case, n, ngp, steps, seed, comp, nr_max_its, eps_max=0.1, dt
     out = dict(n=n, ngp=ngp, nr_max_its=nr_max_its, eps=np.array(eps_hist), sig=np.array(sig), cost=np.array(cost),
                conv=np.array(conv), nl=np.array(nl), elem_type=r.elem_type())
     r.close()
+    if case in MUST_BE_NON_LINEAR:
+        assert out["nl"][-1].all(), f"{case}: every Gauss point of the history must end non-linear"
     return out
 
 
@@ -106,12 +113,16 @@ def main():
         r.close()
     np.savez_compressed(HERE / "elem_type_9x11x10.npz", **et)
     for case, dims, seed in (("damage_sphere", (5, 6, 4), 11), ("plastic_layer", (4, 5, 6), 21),
-                             ("elastic_sphere", (6, 5, 5), 31), ("mic3d_8", (6, 6, 5), 41)):
+                             ("elastic_sphere", (6, 5, 5), 31), ("mic3d_8", (6, 6, 5), 41),
+                             ("plastic_layer_yield", (5, 6, 4), 51)):
         np.savez_compressed(HERE / f"stages_{case}.npz", **stage_fixture(case, dims, seed))
     np.savez_compressed(HERE / "history_damage_sphere.npz",
                         **history_fixture("damage_sphere", 6, 3, 8, 1234, 0, 12))
     np.savez_compressed(HERE / "history_plastic_layer.npz",
                         **history_fixture("plastic_layer", 6, 2, 10, 7, 1, 8, inc=0.01, reverse_after=6))
+    # J2 plasticity that really yields: load for 7 steps, then unload (test/test3d_4.cpp:80-85 pattern) in eps_33
+    np.savez_compressed(HERE / "history_plastic_layer_yield.npz",
+                        **history_fixture("plastic_layer_yield", 7, 3, 12, 17, 2, 12, inc=0.0015, reverse_after=7))
     np.savez_compressed(HERE / "history_elastic_sphere.npz",
                         **history_fixture("elastic_sphere", 8, 4, 2, 5, 0, 4, eps_max=0.01))
     # linear homogenized tangent of the constructor (src/micropp.cpp:256-284)

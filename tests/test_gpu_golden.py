@@ -44,7 +44,8 @@ def test_colouring_contract(mpp):
                 assert mpp.elem_colour(ex, ey, ez) == O.elem_colour(ex, ey, ez) == (ex & 1) + 2 * (ey & 1) + 4 * (ez & 1)
 
 
-@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "mic3d_8"])
+@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "mic3d_8",
+                                  "plastic_layer_yield"])
 def test_stage_fixtures(mpp, case):
     f = load(f"stages_{case}.npz")
     dims = tuple(int(v) for v in f["dims"])
@@ -74,7 +75,7 @@ def test_stage_fixtures(mpp, case):
     assert relerr(g2.ave_stress(un), f["nr_sig"]) < 1e-8
 
 
-@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere"])
+@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "plastic_layer_yield"])
 def test_history_fixtures(mpp, case):
     f = load(f"history_{case}.npz")
     n, ngp, nr = int(f["n"]), int(f["ngp"]), int(f["nr_max_its"])
@@ -90,6 +91,8 @@ def test_history_fixtures(mpp, case):
             assert abs(m.get_cost(gp) - int(f["cost"][k, gp])) <= nr, (k, gp, m.get_cost(gp), int(f["cost"][k, gp]))
             assert relerr(sig[gp], f["sig"][k, gp]) < 1e-8, (k, gp)
         m.update_vars()
+    if case in ("damage_sphere", "plastic_layer_yield"):
+        assert f["nl"][-1].all()  # the fixture (and therefore the product) went through the non-linear branch
 
 
 def test_ctan_lin_fixture(mpp):

@@ -63,7 +63,9 @@ def test_set_displ_bc(mpp, refpy, dims):
 
 @pytest.mark.parametrize("case,with_vars", [("elastic_sphere", False), ("damage_sphere", False),
                                             ("damage_sphere", True), ("plastic_layer", False),
-                                            ("plastic_layer", True), ("mic3d_8", True)])
+                                            ("plastic_layer", True), ("mic3d_8", True),
+                                            ("plastic_layer_yield", False), ("plastic_layer_yield", True),
+                                            ("plastic_fibre_yield", True)])
 def test_assembly_rhs(mpp, refpy, case, with_vars):
     g, r = pair(mpp, refpy, case, (7, 6, 8), calc_ctan_lin=False)
     u = random_u(g.nndim, 2, 5e-3)
@@ -75,7 +77,9 @@ def test_assembly_rhs(mpp, refpy, case, with_vars):
 
 
 @pytest.mark.parametrize("case,with_vars", [("elastic_sphere", False), ("damage_sphere", False),
-                                            ("damage_sphere", True), ("plastic_layer", True), ("mic3d_8", True)])
+                                            ("damage_sphere", True), ("plastic_layer", True), ("mic3d_8", True),
+                                            ("plastic_layer_yield", False), ("plastic_layer_yield", True),
+                                            ("plastic_fibre_yield", True)])
 def test_assembly_mat(mpp, refpy, case, with_vars):
     g, r = pair(mpp, refpy, case, (6, 7, 5), calc_ctan_lin=False)
     u = random_u(g.nndim, 4, 5e-3)
@@ -87,7 +91,7 @@ def test_assembly_mat(mpp, refpy, case, with_vars):
 
 
 def test_ave_stress_and_vars_new(mpp, refpy):
-    for case in ("damage_sphere", "plastic_layer"):
+    for case in ("damage_sphere", "plastic_layer", "plastic_layer_yield"):
         g, r = pair(mpp, refpy, case, (6, 6, 6), calc_ctan_lin=False)
         u = random_u(g.nndim, 6, 2e-2)
         v = random_vars(r.nelem, mat_types(r), 7)
@@ -117,7 +121,7 @@ def test_ell_mvp_and_cg(mpp, refpy):
     assert abs(eg - er) <= 1e-6 * abs(er)
 
 
-@pytest.mark.parametrize("case", ["elastic_sphere", "damage_sphere", "plastic_layer"])
+@pytest.mark.parametrize("case", ["elastic_sphere", "damage_sphere", "plastic_layer", "plastic_layer_yield"])
 def test_newton(mpp, refpy, case):
     g, r = pair(mpp, refpy, case, 9, calc_ctan_lin=False, nr_max_its=6)
     eps = np.array([0.01, -0.004, 0.002, 0.006, -0.003, 0.001]) * (1.0 if case != "elastic_sphere" else 0.1)
@@ -249,6 +253,27 @@ def test_homogenize_plastic_history(mpp, refpy):
     compare_histories(run_history(g, path), run_history(r, path), newton_budget=10)
 
 
+@pytest.mark.parametrize("case,comp", [("plastic_layer_yield", 2), ("plastic_fibre_yield", 1)])
+def test_homogenize_plastic_yield_load_unload(mpp, refpy, case, comp):
+    """J2 plasticity that REALLY yields (E = 3e7, Sy = 1e5: the reference's golden plastic material and bench.py's
+    plastic40 material): heterogeneous RVE, load for 7 steps then unload (test/test3d_4.cpp:80-85), against the compiled
+    reference -- src/material.cpp:111-186 (return mapping, evolute) and :49-63 (forward-difference tangent in the
+    yielded state) through k_elem_rhs / k_elem_ctan / k_asm_mat_general / k_vars_new and a DPCG solve per Newton step."""
+    ngp = 3
+    kw = dict(ngp=ngp, lin_stress=False, calc_ctan_lin=False, nr_max_its=12)
+    g, r = pair(mpp, refpy, case, 9, **kw)
+    scale = np.random.default_rng(17).uniform(0.5, 1.5, ngp)
+    path, e = [], np.zeros((ngp, 6))
+    for k in range(12):
+        e = e.copy()
+        e[:, comp] += (0.0015 if k < 7 else -0.0015) * scale
+        path.append(e)
+    hg, hr = run_history(g, path), run_history(r, path)
+    assert all(hr[-1]["nl"]) and any(hr[3]["nl"])          # the reference itself went plastic on the way up
+    assert len({c for h in hr for c in h["cost"]}) > 3     # ... and the work per step changed with the plastic state
+    compare_histories(hg, hr, newton_budget=12)
+
+
 def test_homogenize_defaults_lin_stress_and_ctan_lin(mpp, refpy):
     # defaults of the C/Fortran entry (SURVEY 3.4): lin_stress=true, calc_ctan_lin=true
     g, r = pair(mpp, refpy, "damage_sphere", 6, ngp=2)
@@ -269,13 +294,81 @@ def test_homogenize_fe_full_and_subiterations(mpp, refpy):
     compare_histories(hg, hr, newton_budget=40)
 
 
-def test_gp_independence(mpp):
+def test_fe_full_ctan_values(mpp, refpy):
+    """FE_FULL homogenized tangent (src/homogenize.cpp:252-276) compared VALUE by value.  ctan[:, i] =
+    (sigma(eps + 1e-8 e_i) - sigma(eps)) / 1e-8 amplifies any difference in sigma by 1e8, so both sides solve the
+    Newton systems to the limit (nr_rel_tol = 1e-10, nr_max_its = 20; DPCG gains 1e-5 per Newton step): what is left
+    is rounding (different summation orders), about 1e-16 |sigma| / 1e-8."""
+    ngp = 3
+    cpl = [mpp.FE_FULL, mpp.FE_FULL, mpp.FE_ONE_WAY]
+    kw = dict(ngp=ngp, coupling=cpl, lin_stress=False, calc_ctan_lin=True, nr_max_its=20, nr_rel_tol=1e-10)
+    for case, n in (("damage_sphere", 7), ("plastic_layer_yield", 6)):
+        g, r = pair(mpp, refpy, case, n, **kw)
+        path = load_path(ngp, 7, 23, comp=(2 if case.startswith("plastic") else 0), eps_max=0.1)
+        hg, hr = run_history(g, path), run_history(r, path)
+        assert hr[-1]["nl"][0] and hr[-1]["nl"][1]
+        worst = 0.0
+        for k, (a, b) in enumerate(zip(hg, hr)):
+            assert a["nl"] == b["nl"] and a["conv"] == b["conv"], k
+            for gp in range(ngp):
+                assert relerr(a["sig"][gp], b["sig"][gp]) < 1e-10, (case, k, gp)
+                worst = max(worst, relerr(a["ctan"][gp], b["ctan"][gp]))
+        print(f"FE_FULL ctan {case}: worst relative difference to the reference {worst:.3e}")
+        assert worst < 1e-6, (case, worst)
+        # the tangent really is the non-linear one (differs from the linear ctan of the constructor)
+        assert relerr(hg[-1]["ctan"][0], g.ctan_lin()) > 1e-3
+
+
+@pytest.mark.parametrize("case,its_A0", [("damage_sphere", 1), ("damage_sphere", 2), ("plastic_layer_yield", 1)])
+def test_use_A0_non_elastic(mpp, refpy, case, its_A0):
+    """use_A0 (src/solve.cpp:56-66, test/test_A0.cpp): the first its_with_A0 Newton iterations of every solve use the
+    shared LINEAR Jacobian assembled once in the constructor (OP_SHARED on the device) -- on a damage / plastic RVE,
+    where that matrix differs from the current tangent, so iteration counts and paths really depend on it."""
+    ngp = 3
+    kw = dict(ngp=ngp, lin_stress=False, calc_ctan_lin=False, nr_max_its=12, use_A0=True, its_with_A0=its_A0)
+    g, r = pair(mpp, refpy, case, 8, **kw)
+    g0, _ = pair(mpp, refpy, case, 8, **dict(kw, use_A0=False))
+    path = load_path(ngp, 8, 1234, comp=(2 if case.startswith("plastic") else 0))
+    hg, hr, h0 = run_history(g, path), run_history(r, path), run_history(g0, path)
+    assert all(hr[-1]["nl"])
+    compare_histories(hg, hr, newton_budget=12)
+    # A0 changed the work (otherwise this test would not test anything)
+    assert [h["cost"] for h in hg] != [h["cost"] for h in h0]
+
+
+def test_write_log_file(mpp, refpy, tmp_path, monkeypatch):
+    """write_log (src/output.cpp:265-282, file opened in the constructor src/micropp.cpp:168-175): same file name, same
+    bytes as the reference's log for the same history."""
+    kw = dict(ngp=3, lin_stress=False, calc_ctan_lin=False, nr_max_its=12, write_log=True, mpi_rank=0)
+    path = load_path(3, 6, 4)
+    texts = []
+    for name, mod in (("ours", mpp), ("ref", refpy)):
+        d = tmp_path / name
+        d.mkdir()
+        monkeypatch.chdir(d)
+        o = (mod.Micropp3 if mod is mpp else mod.RefMicropp)(mk(mod, "damage_sphere", 6, **kw))
+        h = run_history(o, path)
+        o.close()
+        texts.append(((d / "micropp-profiling-0.log").read_text(), h))
+    (to, ho), (tr, hr) = texts
+    assert to.splitlines()[0] == tr.splitlines()[0] == "#<gp_id>  <non-linear>  <cost>  <converged>"
+    assert len(to.splitlines()) == len(tr.splitlines()) == 1 + 6 * 4
+    if [h["cost"] for h in ho] == [h["cost"] for h in hr]:
+        assert to == tr
+    else:  # a CG count may differ by one: every other field must still be identical
+        for lo, lr in zip(to.splitlines(), tr.splitlines()):
+            fo, fr = lo.split(), lr.split()
+            assert fo[:2] == fr[:2] and fo[3:] == fr[3:], (lo, lr)
+
+
+@pytest.mark.parametrize("case", ["plastic_fibre", "plastic_fibre_yield"])
+def test_gp_independence(mpp, case):
     # test/test3d_4.cpp:109-115: identical strains => identical results on every GP
     m = mpp.Micropp3(mpp.default_params(size=(5, 5, 5), ngp=5, lin_stress=False, calc_ctan_lin=False,
-                                        **CASES["plastic_fibre"]))
+                                        **CASES[case]))
     e = np.zeros(6)
     for k in range(6):
-        e[1] += 0.01
+        e[1] += 0.01 if case == "plastic_fibre" else 0.002
         for gp in range(5):
             m.set_strain(gp, e)
         m.homogenize()
@@ -407,14 +500,15 @@ def test_bench_damage_workload_against_reference(mpp, refpy):
     assert any(hg[-1]["nl"])                 # the path does reach the damage branch
 
 
-@pytest.mark.parametrize("case,steps", [("damage_sphere", 7), ("elastic_sphere", 2), ("plastic_layer", 5)])
+@pytest.mark.parametrize("case,steps", [("damage_sphere", 7), ("elastic_sphere", 2), ("plastic_layer", 5),
+                                        ("plastic_layer_yield", 7)])
 def test_multi_wave_equals_single_wave(mpp, monkeypatch, case, steps):
     """More Gauss points than resident slots (MICROPP_WAVE caps the wave; at BASELINE sizes 4096 damage RVEs of 50^3 do
     not fit one GPU at once): the Gauss points are processed wave by wave with their FE state parked in HBM between
     waves -- results, costs and flags must be bit-identical to the all-resident run."""
     ngp = 7
     kw = dict(ngp=ngp, lin_stress=False, calc_ctan_lin=False, nr_max_its=12)
-    path = load_path(ngp, steps, 99, comp=(1 if case == "plastic_layer" else 0),
+    path = load_path(ngp, steps, 99, comp=(1 if case == "plastic_layer" else 2 if case == "plastic_layer_yield" else 0),
                      eps_max=(1.0 if case == "plastic_layer" else 0.1))
     monkeypatch.setenv("MICROPP_WAVE", "3")
     a = mpp.Micropp3(mk(mpp, case, 7, **kw))

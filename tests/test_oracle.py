@@ -154,7 +154,8 @@ def test_elem_type_fixture():
         assert np.array_equal(O.elem_types(mt, (0.2, 0.1, 0.1, 0.1), (9, 11, 10)), f[f"type{mt}"]), mt
 
 
-@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "mic3d_8"])
+@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "mic3d_8",
+                                  "plastic_layer_yield"])
 def test_stage_fixtures(case):
     f = load(f"stages_{case}.npz")
     dims = tuple(int(v) for v in f["dims"])
@@ -182,7 +183,7 @@ def test_stage_fixtures(case):
     assert relerr(o.ave_stress(un), f["nr_sig"]) <= 1e-12
 
 
-@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere"])
+@pytest.mark.parametrize("case", ["damage_sphere", "plastic_layer", "elastic_sphere", "plastic_layer_yield"])
 def test_history_fixtures(case):
     f = load(f"history_{case}.npz")
     n, ngp = int(f["n"]), int(f["ngp"])
@@ -221,3 +222,19 @@ def test_oracle_vs_compiled_reference_live(refpy):
         eps = rng.uniform(-1, 1, 6) * 10.0 ** rng.uniform(-5, -1)
         assert np.array_equal(O.mat_stress(m, eps), refpy.mat_stress(m, eps))
         assert np.array_equal(O.mat_ctan(m, eps), refpy.mat_ctan(m, eps))
+
+
+# ------------------------------------------------------------------ full-size fixtures: inputs are bench.py's own
+@pytest.mark.parametrize("workload", ["damage50", "plastic40"])
+def test_full_size_fixture_inputs_are_the_bench_load_path(workload):
+    """tests/golden/bench_<workload>_2gp.npz (reference run at the bench size, make_golden_full.py) was generated from
+    the very strains bench.py feeds the product, and its Gauss points end non-linear."""
+    import bench
+    f = load(f"bench_{workload}_2gp.npz")
+    wl = bench.WORKLOADS[workload]
+    assert int(f["n"]) == wl["n"]
+    gps = [int(g) for g in f["gps"]]
+    for k in range(f["eps"].shape[0]):
+        assert np.array_equal(f["eps"][k], bench.strains_for(workload, wl["ngp"], 0, k)[gps])
+    assert f["nl"][-1].all() and np.all(np.isfinite(f["sig"]))
+    assert f["eps"].shape[0] == wl["prep_steps"] + 1          # the fixture covers the step bench.py times

@@ -106,12 +106,22 @@ def test_balanced_ranges_cost_aware():
     """(f) rank 4: contiguous cost-aware shards (test/mpi-load-balance.cpp:56-73: 25 % non-linear GPs cost 3-5x)."""
     from micropp_b200.sharding import balanced_ranges, gp_range
     # equal costs => the reference drivers' rule
-    for ngp, nproc in ((16, 4), (10, 3), (7, 8)):
+    for ngp, nproc in ((16, 4), (10, 3), (7, 8), (10, 4), (9, 4), (1, 3), (4096, 8)):
         got = balanced_ranges([5] * ngp, nproc)
-        assert [e - b for b, e in got if e > b] == [gp_range(ngp, nproc, r)[1] - gp_range(ngp, nproc, r)[0]
-                                                   for r in range(nproc) if gp_range(ngp, nproc, r)[1] > gp_range(ngp, nproc, r)[0]] \
-            or max(e - b for b, e in got) <= -(-ngp // nproc)
-        assert got[0][0] == 0 and max(e for _, e in got) == ngp
+        assert got == [gp_range(ngp, nproc, r) for r in range(nproc)], (ngp, nproc, got)
+    # unequal costs: contiguous cover, bottleneck optimal (checked against brute force), parts even
+    import itertools
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        ngp, nproc = int(rng.integers(3, 11)), int(rng.integers(2, 5))
+        costs = [int(c) for c in rng.integers(0, 50, ngp)]
+        got = balanced_ranges(costs, nproc)
+        assert len(got) == nproc and got[0][0] == 0 and got[-1][1] == ngp
+        assert all(got[i][1] == got[i + 1][0] for i in range(nproc - 1))
+        w = [c + 1.0 for c in costs]
+        best = min(max(sum(w[b:e]) for b, e in zip((0,) + cut, cut + (ngp,)))
+                   for cut in itertools.combinations_with_replacement(range(ngp + 1), nproc - 1))
+        assert max(sum(w[b:e]) for b, e in got) <= best * (1 + 1e-9), (costs, nproc, got)
     # the reference's imbalance scenario: the first quarter of the GPs is non-linear and 4x as expensive
     costs = [400] * 16 + [100] * 48
     parts = balanced_ranges(costs, 4)
