@@ -17,6 +17,12 @@ through the reference-facing C ABI of libmicropp_b200.so.  Workloads (BASELINE.j
 
 Scaling is weak: every rank owns its own GPs (independent RVEs -- no data-path collective).
 
+One invocation also measures, after the headline workload and inside the same JSON line (`workloads`), bounded
+shards of the other BASELINE configs on the same GPUs: `damage50` and `plastic40` (fewer Gauss points per GPU, stated
+in each entry; same keys as the headline: value, e2e, roofline, cpu_baseline) and `slab200` (ONE 200^3 elastic RVE over
+z-slabs on all N GPUs: ms per solve, DPCG iterations).  `--no-extra` skips them; `--workload X` makes X the headline.
+`--full-path` times the whole load path (every load step with update_vars) instead of a repeated single step.
+
 JSON keys beyond the base contract:
   value      GP/s with the device-event time of homogenize() (CUDA events on the library's stream, max over ranks)
   e2e        GP/s with host buffers through the C ABI: set_strains(host) + homogenize + get_stresses(host), wall clock
@@ -162,8 +168,12 @@ def spmv_bytes_per_rve(n: int) -> tuple[float, float]:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, wl, sample_ngp: int, steps: int, warmup: int):
-    """The reference's own CPU path (oracle/_ref, OpenMP over GPs) on a bounded sample of the workload."""
+def run_reference(name, wl, sample_ngp: int, steps: int, warmup: int, restart_from=None):
+    """The reference's own CPU path (oracle/_ref, OpenMP over GPs) on a bounded sample of the workload.
+
+    restart_from=(directory, id): the internal state at the start of the timed load step is read from a restart file in
+    the reference's own format (src/output.cpp:217-262) instead of being recomputed on the CPU -- the preparation steps
+    of damage50 / plastic40 take minutes there."""
     from oracle import refpy
     if not refpy.available(omp=True):
         raise RuntimeError("oracle/_ref/libmicropp_ref_omp.so missing: run `make -C oracle ref` where "
@@ -173,52 +183,392 @@ def run_reference(args, wl, sample_ngp: int, steps: int, warmup: int):
     os.environ["OMP_NUM_THREADS"] = os.environ.get("MICROPP_REF_THREADS", str(cores))
     n = wl["n"]
     p = refpy.default_params(size=(n, n, n), ngp=sample_ngp, **wl["params"])
-    r = refpy.RefMicropp(p, omp=True)
-    name = args.workload
+    cwd = os.getcwd()
+    if restart_from is not None:
+        os.chdir(restart_from[0])
+    try:
+        r = refpy.RefMicropp(p, omp=True)
 
-    def step(k):
-        e = strains_for(name, sample_ngp, 0, k)
-        for g in range(sample_ngp):
-            r.set_strain(g, e[g])
-        r.homogenize()
-        return np.array([r.get_stress(g) for g in range(sample_ngp)])
+        def step(k):
+            e = strains_for(name, sample_ngp, 0, k)
+            for g in range(sample_ngp):
+                r.set_strain(g, e[g])
+            r.homogenize()
+            return np.array([r.get_stress(g) for g in range(sample_ngp)])
+
+        if restart_from is not None:
+            r.read_restart(restart_from[1])
+        else:
+            for k in range(wl["prep_steps"]):
+                step(k)
+                r.update_vars()
+        kk = wl["prep_steps"]
+        for _ in range(warmup):
+            step(kk)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sig = step(kk)
+        dt = time.perf_counter() - t0
+        cost = [r.get_cost(g) for g in range(sample_ngp)]
+        r.close()
+    finally:
+        os.chdir(cwd)
+    threads = min(int(os.environ["OMP_NUM_THREADS"]), sample_ngp)
+    return dict(value=sample_ngp * steps / dt, ms_per_step=dt / steps * 1e3, cores=threads, stress=sig,
+                sample=f"{sample_ngp} of the workload's GPs per step, {steps} timed step(s) after {warmup} warm-up; "
+                       f"mean CG its/GP {np.mean(cost):.1f}; OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']} "
+                       f"({threads} busy: one RVE per thread)"
+                       + ("; state at the start of the timed load step read from a restart file in the reference's "
+                          "format (written by the product after the preparation steps)" if restart_from else ""))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+class Env:
+    """process-group plumbing (torch.distributed over NCCL): barrier + reductions of the timings, nothing else"""
+
+    def __init__(self, torch, dist, world, rank, local_rank):
+        self.torch, self.dist, self.world, self.rank, self.local_rank = torch, dist, world, rank, local_rank
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+
+def spmv_roofline(name, n, prof, prof_ms, apps, implicit_kernel, nsteps):
+    """roofline of the DPCG SpMV (+ the DPCG vector kernels) from the instrumented repeat (CUDA events per launch)"""
+    peak, peak_src = hbm_peak()
+    spmv_ms = prof["spmv_ms"]
+    sec = max(spmv_ms, 1e-9) * 1e-3
+    common = {"rve_applications": apps, "launches": prof["spmv_launches"], "kernel_ms": spmv_ms,
+              "share_of_step": spmv_ms / max(prof_ms, 1e-9), "instrumented_step_ms": prof_ms / nsteps,
+              "other_kernels_ms": {"asm_mat": prof["asm_mat_ms"], "asm_rhs": prof["asm_rhs_ms"],
+                                   "cg_vectors": prof["cg_vec_ms"]}}
+    if implicit_kernel >= 0:
+        # all-elastic RVE: the Jacobian is never stored per RVE; the SpMV moves only p and Ap and is bound by the
+        # FP64 pipe (243 DFMA per interior node), so BOTH fractions are reported; `frac` stays the HBM one
+        b_alg = spmv_imp_bytes_per_rve(n)
+        flops = 2.0 * 243.0 * (n - 2) ** 3
+        achieved = b_alg * apps / sec / 1e9
+        kname = {0: "k_spmv_dot_imp<8>", 3: "k_spmv_dot_tmac"}.get(implicit_kernel, f"implicit kernel {implicit_kernel}")
+        key = "implicit_" + {0: "simple", 3: "tmac"}.get(implicit_kernel, str(implicit_kernel))
+        r = {"kernel": kname + " (DPCG SpMV + p.Ap on the implicit elastic operator: no matrix stream)",
+             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+             "peak_source": peak_src, "traffic": None, "bytes_per_rve_application": b_alg,
+             "limiter": "fp64 pipe, not HBM: the 1944 B/node matrix stream of the assembled path is eliminated, "
+                        "not moved faster (see roofline_assembled for the HBM-bound SpMV of the same workload)",
+             "fp64": {"achieved_tflops": flops * apps / sec / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
+                      "frac": flops * apps / sec / 1e12 / FP64_PEAK_TFLOPS,
+                      "peak_source": "nominal: 148 SM x 64 DFMA/clk x 1965 MHz"},
+             "equivalent_664": 664.0 * 3 * n ** 3 * apps / sec / 1e9}
+    else:
+        b_alg, b_664 = spmv_bytes_per_rve(n)
+        achieved = b_alg * apps / sec / 1e9
+        key = "assembled"
+        r = {"kernel": "k_spmv_dot (DPCG SpMV + p.Ap, one assembled ELL matrix per RVE)", "bound": "hbm",
+             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+             "traffic": None, "achieved_664": b_664 * apps / sec / 1e9, "bytes_per_rve_application": b_alg}
+    # the DPCG vector kernels (cg_update + cg_pupdate, HBM-bound streams; cg_init / cg_finish / u += du are in the
+    # same timer but run once per Newton step): bytes per node and iteration from DESIGN.md section 5
+    vec_b = (76.0 + 124.0 if implicit_kernel >= 0 else 120.0 + 120.0) * n ** 3
+    vec_sec = max(prof["cg_vec_ms"], 1e-9) * 1e-3
+    common["dpcg_vector_kernels"] = {"bound": "hbm", "achieved": vec_b * apps / vec_sec / 1e9, "peak": peak,
+                                     "unit": "GB/s", "frac": vec_b * apps / vec_sec / 1e9 / peak,
+                                     "bytes_per_rve_iteration": vec_b,
+                                     "share_of_step": prof["cg_vec_ms"] / max(prof_ms, 1e-9)}
+    r.update(common)
+    # `traffic` cannot be measured inside a timed run (DRAM counters need ncu's kernel replay): it is the per-RVE DRAM
+    # byte count of the committed `ncu --set full` capture of the same kernel, scaled to this run's launches
+    tr = ROOT / "profiles" / "spmv_traffic.json"
+    if tr.exists():
+        try:
+            ent = json.loads(tr.read_text())[name][key]
+            r["traffic"] = ent["dram_bytes_per_rve_application"] * apps / max(prof["spmv_launches"], 1)
+            r["traffic_source"] = "from profiles/: " + ent.get("source", "profiles/spmv_traffic.json") + \
+                                  " (dram__bytes_read.sum + dram__bytes_write.sum per RVE application, not measured live)"
+            r["algorithmic_bytes_per_launch"] = b_alg * apps / max(prof["spmv_launches"], 1)
+        except Exception:
+            pass
+    return r
+
+
+def run_b200_workload(M, env: Env, name: str, ngp: int, steps: int, warmup: int, *, cpu_baseline: bool,
+                      cpu_sample, assembled_repeat: bool, full_path: bool = False):
+    """One workload on this rank's GPU; returns the entry (headline line fields or a `workloads` entry)."""
+    import ctypes as C
+    torch = env.torch
+    wl = WORKLOADS[name]
+    n = wl["n"]
+    rank, local_rank, world = env.rank, env.local_rank, env.world
+    cfg = {"workload": wl["label"] if ngp == wl["ngp"] else wl["label"] + f" -- bounded shard of {ngp} GPs/GPU",
+           "name": name, "rve_nodes": f"{n}^3", "gps_per_gpu": ngp, "coupling": "FE_ONE_WAY",
+           "sharding": "independent GPs per rank, no collective",
+           "l2": "inputs exceed L2: every DPCG pass streams the vectors of all resident RVEs (%.1f GB per pass at %d "
+                 "GPs); assembled-matrix path: plus one %.1f MB ELL matrix per RVE"
+                 % (8 * 24.0 * n ** 3 * ngp / 1e9, ngp, 1944.0 * (n - 2) ** 3 / 1e6)}
+    t_ctor = time.perf_counter()
+    m = M.Micropp3(M.default_params(size=(n, n, n), ngp=ngp, mpi_rank=local_rank, **wl["params"]))
+    ctor_s = time.perf_counter() - t_ctor
+
+    # pinned host buffers for the boundary crossing (the C ABI takes plain host pointers)
+    eps_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
+    sig_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
+    eps_h, sig_h = eps_pin.numpy(), sig_pin.numpy()
+    dp = C.POINTER(C.c_double)
+    h = C.byref(m.h)
+    lib = m.lib
+
+    def e2e_step(k):
+        # micropp3_set_strains / micropp3_get_stresses ARE the macro code's loop: `for gp: set_strain(gp, eps+6gp)` /
+        # `for gp: get_stress(gp, sig+6gp)` compiled in C (micropp_host.cpp), i.e. the reference's per-GP calls without
+        # a Python interpreter in between
+        eps_h[:] = strains_for(name, ngp, rank, k)
+        lib.micropp3_set_strains(h, eps_h.ctypes.data_as(dp))
+        lib.micropp3_homogenize(h)
+        lib.micropp3_get_stresses(h, sig_h.ctypes.data_as(dp))
+
+    if full_path:
+        # the whole load path, every step with update_vars (GPs turn non-linear at different steps)
+        nsteps = wl["prep_steps"] + 4 if wl["prep_steps"] else 1
+        sampler = ClockSampler(local_rank)
+        env.barrier()
+        sampler.start()
+        l0 = m.launch_count()
+        per_step, t0 = [], time.perf_counter()
+        for k in range(nsteps):
+            e2e_step(k)
+            per_step.append({"step": k, "dev_ms": env.max(m.last_homogenize_ms()),
+                             "non_linear_gps": int(env.sum(float(m.get_non_linear_gps()))),
+                             "mean_cg_its": env.sum(float(np.sum([m.get_cost(g) for g in range(ngp)]))) / (ngp * world)})
+            m.update_vars()
+        env.barrier()
+        wall = env.max(time.perf_counter() - t0)
+        clocks = sampler.stop()
+        launches = int(env.sum(float(m.launch_count() - l0)))
+        tot = env.sum(float(ngp))
+        dev = sum(p["dev_ms"] for p in per_step)
+        m.close()
+        return {"value": tot * nsteps / (dev * 1e-3), "unit": "GP-steps/s", "ms_per_step": dev / nsteps, "steps": nsteps,
+                "config": dict(cfg, path=f"load steps 0..{nsteps - 1} with update_vars after each"),
+                "e2e": {"value": tot * nsteps / wall, "unit": "GP-steps/s", "h2d_bytes_per_step": int(ngp * 48),
+                        "d2h_bytes_per_step": int(ngp * 48), "ms_per_step": wall / nsteps * 1e3},
+                "per_step": per_step, "gpu_launches": launches, "clocks": clocks}
 
     for k in range(wl["prep_steps"]):
-        step(k)
-        r.update_vars()
+        e2e_step(k)
+        m.update_vars()
     kk = wl["prep_steps"]
     for _ in range(warmup):
-        step(kk)
+        e2e_step(kk)
+
+    # ---- timed region 1: device-event time of homogenize() with the strains already handed over ----
+    sampler = ClockSampler(local_rank)
+    env.barrier()
+    sampler.start()
+    launches0 = m.launch_count()
+    dev_ms = 0.0
+    for _ in range(steps):
+        lib.micropp3_homogenize(h)
+        dev_ms += m.last_homogenize_ms()
+    env.barrier()
+    launches = m.launch_count() - launches0
+    cost = np.array([m.get_cost(g) for g in range(ngp)], dtype=np.float64)
+    conv = sum(m.has_converged(g) for g in range(ngp))
+    nl = m.get_non_linear_gps()
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ----
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step(kk)
-    dt = time.perf_counter() - t0
-    cost = [r.get_cost(g) for g in range(sample_ngp)]
-    r.close()
-    return dict(value=sample_ngp * steps / dt, ms_per_step=dt / steps * 1e3, cores=cores,
-                sample=f"{sample_ngp} of the workload's GPs per step, {steps} timed step(s) after {warmup} warm-up; "
-                       f"mean CG its/GP {np.mean(cost):.1f}; OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}")
+        e2e_step(kk)
+    env.barrier()
+    wall2 = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.all(np.isfinite(sig_h)), "non-finite homogenized stress"
+    sig_gpu = sig_h.copy()
+
+    # ---- instrumented repeat of the same steps: CUDA events around every kernel launch (plain stream launches) ----
+    m.prof_enable(True)
+    m.prof_read(True)
+    prof_dev_ms = 0.0
+    for _ in range(steps):
+        lib.micropp3_homogenize(h)
+        prof_dev_ms += m.last_homogenize_ms()
+    prof = m.prof_read(True)
+    m.prof_enable(False)
+
+    dev_ms_max = env.max(dev_ms)
+    wall2_max = env.max(wall2)
+    total_gps = env.sum(float(ngp))
+    launches_tot = int(env.sum(float(launches)))
+
+    # roofline of the dominant kernel (rank 0's launches; every SpMV application of an RVE = one CG iteration)
+    apps = float(np.sum(cost)) * steps
+    imp_kernel = m.implicit_kernel()
+    roof = spmv_roofline(name, n, prof, prof_dev_ms, apps, imp_kernel, steps)
+
+    # all-elastic workloads: the same workload once more through the assembled-matrix path (MICROPP_IMPLICIT=0) on a
+    # bounded batch, instrumented, so that the HBM-bound SpMV the north star names is measured in the same run
+    roof_asm = None
+    if imp_kernel >= 0 and rank == 0 and assembled_repeat:
+        try:
+            ngp_a = min(ngp, 256)
+            os.environ["MICROPP_IMPLICIT"] = "0"
+            ma = M.Micropp3(M.default_params(size=(n, n, n), ngp=ngp_a, mpi_rank=local_rank, **wl["params"]))
+            del os.environ["MICROPP_IMPLICIT"]
+            ea = strains_for(name, ngp, rank, kk)[:ngp_a]
+            ma.set_strains(ea)
+            for _ in range(2):
+                ma.homogenize()
+            ma.prof_enable(True)
+            ma.prof_read(True)
+            ma.homogenize()
+            ms_a = ma.last_homogenize_ms()
+            prof_a = ma.prof_read(True)
+            ma.prof_enable(False)
+            apps_a = float(sum(ma.get_cost(g) for g in range(ngp_a)))
+            roof_asm = spmv_roofline(name, n, prof_a, ms_a, apps_a, -1, 1)
+            roof_asm["gps"] = ngp_a
+            roof_asm["value_gps_per_s"] = ngp_a / (ms_a * 1e-3)
+            sa = ma.get_stresses()
+            roof_asm["max_rel_diff_vs_implicit"] = float(np.max(np.abs(sa - sig_gpu[:ngp_a]) /
+                                                                np.max(np.abs(sa), axis=1, keepdims=True)))
+            ma.close()
+        except Exception as ex:
+            os.environ.pop("MICROPP_IMPLICIT", None)
+            roof_asm = {"unavailable": str(ex)}
+
+    entry = {"value": total_gps * steps / (dev_ms_max * 1e-3), "unit": "GP/s", "steps": steps, "warmup": warmup,
+             "ms_per_step": dev_ms_max / steps,
+             "config": dict(cfg, newton_cg={"mean_cg_its_per_gp": float(np.mean(cost)), "converged": conv,
+                                            "non_linear_gps": nl, "wave": m.wave_size()}, ctor_s=ctor_s),
+             "e2e": {"value": total_gps * steps / wall2_max, "unit": "GP/s", "h2d_bytes_per_step": int(ngp * 48),
+                     "d2h_bytes_per_step": int(ngp * 48), "ms_per_step": wall2_max / steps * 1e3,
+                     "api": "micropp3_set_strains + micropp3_homogenize + micropp3_get_stresses on host buffers: the "
+                            "first and last are C loops over the reference's per-GP set_strain / get_stress"},
+             "gpu_launches": launches_tot, "clocks": clocks, "roofline": roof}
+    if roof_asm is not None:
+        entry["roofline_assembled"] = roof_asm
+
+    if rank == 0 and world == 1 and cpu_baseline:
+        try:
+            cores = host_cores()
+            restart = None
+            if wl["prep_steps"]:
+                # bounded sample: the state after the preparation steps of the sample's GPs is produced by the product
+                # (a second small object: steps 0..prep-1 on the GPU) and handed to the reference as a restart file
+                sample = cpu_sample or min(cores, 8)
+                import tempfile
+                tmp = tempfile.mkdtemp(prefix="micropp_bench_")
+                cwd = os.getcwd()
+                os.chdir(tmp)
+                try:
+                    ms_ = M.Micropp3(M.default_params(size=(n, n, n), ngp=sample, mpi_rank=0, **wl["params"]))
+                    for k in range(wl["prep_steps"]):
+                        ms_.set_strains(strains_for(name, sample, 0, k))
+                        ms_.homogenize()
+                        ms_.update_vars()
+                    ms_.write_restart(1)
+                    ms_.close()
+                finally:
+                    os.chdir(cwd)
+                restart = (tmp, 1)
+            else:
+                sample = cpu_sample or 4 * cores
+            res = run_reference(name, wl, sample, 1, 0, restart_from=restart)
+            if restart is not None:
+                import shutil
+                shutil.rmtree(restart[0], ignore_errors=True)
+            entry["cpu_baseline"] = {"value": res["value"], "unit": "GP/s", "cores": res["cores"], "kind": "reference",
+                                     "sample": res["sample"]}
+            # the sample's GPs are the first GPs of rank 0's batch: same strains => the stresses must agree
+            ref_sig = res["stress"]
+            d = np.max(np.abs(ref_sig - sig_gpu[:sample]), axis=1) / np.maximum(np.max(np.abs(ref_sig), axis=1), 1e-300)
+            entry["cpu_baseline"]["max_rel_stress_diff_vs_gpu"] = float(np.max(d))
+        except Exception as ex:  # the baseline is reported, never required for the GPU number
+            entry["cpu_baseline"] = {"value": None, "unit": "GP/s", "cores": host_cores(), "kind": "reference",
+                                     "sample": f"unavailable: {ex}"}
+    m.close()
+    return entry
+
+
+def run_slab(M, env: Env, n: int, reps: int):
+    """BASELINE configs[4]: ONE n^3 elastic RVE (sphere, contrast 10, eps = {1e-3,0,0,0,0,0}) over z-slabs on all ranks'
+    GPUs (strong scaling): halo planes of p and the DPCG dot products travel over NVLink peer memory."""
+    from micropp_b200.slab import SlabRVE
+    torch = env.torch
+    kw = dict(size=(n, n, n), type=1, geo_params=(0.2, 0, 0, 0), materials=[EL(1e7), EL(1e8), EL(1e7)],
+              lin_stress=False, calc_ctan_lin=False)
+    eps = np.array([1e-3, 0, 0, 0, 0, 0.0])
+    w = (env.dist, env.rank, env.world) if env.world > 1 else None
+    t0 = time.perf_counter()
+    rve = SlabRVE(kw, world=w, nslabs=1, device=env.local_rank)
+    ctor = time.perf_counter() - t0
+    times = []
+    out = None
+    l0 = rve.launch_count()
+    for _ in range(reps + 1):          # the first solve also builds the CUDA graphs: untimed
+        env.barrier()
+        t0 = time.perf_counter()
+        out = rve.homogenize(eps)
+        torch.cuda.synchronize()
+        times.append(env.max(time.perf_counter() - t0))
+    launches = int(env.sum(float(rve.launch_count() - l0)))
+    best = min(times[1:])
+    its = out["cg_its"]
+    entry = {"value": best * 1e3, "unit": "ms per homogenize() of the one RVE", "higher_is_better": False,
+             "scaling": "strong", "n_gpus": env.world, "ms_all": [round(x * 1e3, 2) for x in times],
+             "cg_its": its, "newton_its": out["newton_its"], "converged": out["converged"],
+             "stress": [float(x) for x in out["stress"]], "cg_iteration_us": best * 1e6 / max(its, 1),
+             "config": {"workload": f"configs[4]: single {n}^3-node RVE, elastic sphere contrast 10, z-slabs over "
+                                    f"{env.world} GPU(s), implicit operator", "exchange": rve.exchange,
+                        "halo_bytes_each_way_per_iteration": 24 * n * n, "ctor_s": ctor},
+             "peer_error": rve.peer_error(), "gpu_launches": launches}
+    fx = ROOT / "tests" / "golden" / f"bench_slab{n}.npz"
+    if fx.exists():   # the reference's own result for this RVE (tests/golden/make_golden_full.py)
+        f = np.load(fx)
+        entry["vs_reference_fixture"] = {"stress_relerr": float(np.max(np.abs(out["stress"] - f["sig"])) /
+                                                                np.max(np.abs(f["sig"]))),
+                                         "reference_cg_its": int(f["cost"])}
+    rve.close()
+    return entry
 
 
 # ------------------------------------------------------------------------------------------------ main
+METRIC = "homogenized GPs/sec (DPCG+assembly)"
+EXTRA_NGP = {"damage50": 64, "plastic40": 64, "elastic30": 1024}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="elastic30")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["slab200"], default="elastic30")
     ap.add_argument("--ngp", type=int, default=None, help="GPs per GPU (default: the workload's)")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--cpu-sample", type=int, default=None, help="GPs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-assembled", action="store_true",
                     help="skip the assembled-matrix repeat of an all-elastic workload (roofline_assembled)")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (no `workloads` entries)")
+    ap.add_argument("--extra", default="damage50,plastic40,slab200", help="comma list of the additional workloads")
+    ap.add_argument("--full-path", action="store_true", help="time the whole load path of the workload")
+    ap.add_argument("--slab-n", type=int, default=200)
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    steps = args.steps if args.steps is not None else (20 if args.workload == "elastic30" else 3)
-    warmup = max(args.warmup, 0)
-    ngp = args.ngp or wl["ngp"]
-    n = wl["n"]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,20 +580,26 @@ def main():
                str(Path(__file__).resolve())] + sys.argv[1:]
         os.execv(sys.executable, cmd)
 
-    base_cfg = {"workload": wl["label"], "name": args.workload, "rve_nodes": f"{n}^3", "gps_per_gpu": ngp,
-                "coupling": "FE_ONE_WAY", "sharding": "independent GPs per rank, no collective",
-                "l2": "inputs exceed L2: every DPCG pass streams the vectors of all resident RVEs (%.1f GB per pass "
-                      "at %d GPs); assembled-matrix path: plus one %.1f MB ELL matrix per RVE"
-                      % (8 * 24.0 * n ** 3 * ngp / 1e9, ngp, 1944.0 * (n - 2) ** 3 / 1e6)}
+    warmup = max(args.warmup, 0)
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
+        name = args.workload if args.workload in WORKLOADS else "elastic30"
+        wl = WORKLOADS[name]
+        steps = args.steps if args.steps is not None else (20 if name == "elastic30" else 3)
+        n = wl["n"]
+        ngp = args.ngp or wl["ngp"]
         cores = host_cores()
-        sample = args.cpu_sample or (4 * cores if args.workload == "elastic30" else cores)
-        res = run_reference(args, wl, sample, steps, warmup)
-        line = {"impl": "reference", "metric": "homogenized GPs/sec (DPCG+assembly)", "value": res["value"],
+        sample = args.cpu_sample or (4 * cores if name == "elastic30" else cores)
+        res = run_reference(name, wl, sample, steps, warmup)
+        base_cfg = {"workload": wl["label"], "name": name, "rve_nodes": f"{n}^3", "gps_per_gpu": ngp,
+                    "coupling": "FE_ONE_WAY", "sharding": "independent GPs per rank, no collective",
+                    "l2": "inputs exceed L2: every DPCG pass streams the vectors of all resident RVEs (%.1f GB per pass "
+                          "at %d GPs); assembled-matrix path: plus one %.1f MB ELL matrix per RVE"
+                          % (8 * 24.0 * n ** 3 * ngp / 1e9, ngp, 1944.0 * (n - 2) ** 3 / 1e6)}
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"],
                 "unit": "GP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": base_cfg,
@@ -263,207 +619,51 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = Env(torch, dist, world, rank, local_rank)
 
     import micropp_b200 as M
     M.load()
 
-    def barrier():
+    if args.workload == "slab200":
+        e = run_slab(M, env, args.slab_n, max(args.steps or 2, 1))
+        line = {"metric": "ms per homogenize() of one 200^3 RVE over z-slabs", "warmup": 1, "steps": len(e["ms_all"]) - 1,
+                "ms_per_step": e["value"], "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        line.update(e)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return 0
 
-    t_ctor = time.perf_counter()
-    m = M.Micropp3(M.default_params(size=(n, n, n), ngp=ngp, mpi_rank=local_rank, **wl["params"]))
-    ctor_s = time.perf_counter() - t_ctor
+    name = args.workload
+    wl = WORKLOADS[name]
+    steps = args.steps if args.steps is not None else (20 if name == "elastic30" else 3)
+    ngp = args.ngp or wl["ngp"]
+    entry = run_b200_workload(M, env, name, ngp, steps, warmup, cpu_baseline=not args.no_cpu_baseline,
+                              cpu_sample=args.cpu_sample, assembled_repeat=not args.no_assembled,
+                              full_path=args.full_path)
+    line = {"metric": METRIC, "value": entry.pop("value"), "unit": entry.pop("unit"), "n_gpus": world,
+            "steps": entry.pop("steps"), "warmup": warmup, "ms_per_step": entry.pop("ms_per_step"),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    line.update(entry)
 
-    # pinned host buffers for the boundary crossing (the C ABI takes plain host pointers)
-    eps_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
-    sig_pin = torch.empty((ngp, 6), dtype=torch.float64).pin_memory()
-    eps_h, sig_h = eps_pin.numpy(), sig_pin.numpy()
-
-    import ctypes as C
-    dp = C.POINTER(C.c_double)
-    h = C.byref(m.h)
-    lib = m.lib
-
-    def e2e_step(k):
-        eps_h[:] = strains_for(args.workload, ngp, rank, k)
-        lib.micropp3_set_strains(h, eps_h.ctypes.data_as(dp))
-        lib.micropp3_homogenize(h)
-        lib.micropp3_get_stresses(h, sig_h.ctypes.data_as(dp))
-
-    for k in range(wl["prep_steps"]):
-        e2e_step(k)
-        m.update_vars()
-    kk = wl["prep_steps"]
-    for _ in range(warmup):
-        e2e_step(kk)
-
-    # ---- timed region 1: device-event time of homogenize() with the strains already handed over ----
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = m.launch_count()
-    dev_ms = 0.0
-    for _ in range(steps):
-        lib.micropp3_homogenize(h)
-        dev_ms += m.last_homogenize_ms()
-    barrier()
-    launches = m.launch_count() - launches0
-    cost = np.array([m.get_cost(g) for g in range(ngp)], dtype=np.float64)
-    conv = sum(m.has_converged(g) for g in range(ngp))
-    nl = m.get_non_linear_gps()
-
-    # ---- timed region 2: end to end through the C ABI with host buffers ----
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        e2e_step(kk)
-    barrier()
-    wall2 = time.perf_counter() - t0
-    clocks = sampler.stop()
-    assert np.all(np.isfinite(sig_h)), "non-finite homogenized stress"
-
-    # ---- instrumented repeat of the same steps: CUDA events around every kernel launch (plain stream launches) ----
-    m.prof_enable(True)
-    m.prof_read(True)
-    prof_dev_ms = 0.0
-    for _ in range(steps):
-        lib.micropp3_homogenize(h)
-        prof_dev_ms += m.last_homogenize_ms()
-    prof = m.prof_read(True)
-    m.prof_enable(False)
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    dev_ms_max = max_over_ranks(dev_ms)
-    wall2_max = max_over_ranks(wall2)
-    total_gps = sum_over_ranks(float(ngp))
-    launches_tot = int(sum_over_ranks(float(launches)))
-
-    # roofline of the dominant kernel (rank 0's launches; every SpMV application of an RVE = one CG iteration)
-    apps = float(np.sum(cost)) * steps
-    peak, peak_src = hbm_peak()
-    imp_kernel = m.implicit_kernel()
-
-    def spmv_roofline(prof, prof_ms, apps, implicit_kernel, nsteps):
-        spmv_ms = prof["spmv_ms"]
-        sec = max(spmv_ms, 1e-9) * 1e-3
-        common = {"rve_applications": apps, "launches": prof["spmv_launches"], "kernel_ms": spmv_ms,
-                  "share_of_step": spmv_ms / max(prof_ms, 1e-9), "instrumented_step_ms": prof_ms / nsteps,
-                  "other_kernels_ms": {"asm_mat": prof["asm_mat_ms"], "asm_rhs": prof["asm_rhs_ms"],
-                                       "cg_vectors": prof["cg_vec_ms"]}}
-        if implicit_kernel >= 0:
-            # all-elastic RVE: the Jacobian is never stored per RVE; the SpMV moves only p and Ap and is bound by the
-            # FP64 pipe (243 DFMA per interior node), so BOTH fractions are reported; `frac` stays the HBM one
-            b_alg = spmv_imp_bytes_per_rve(n)
-            flops = 2.0 * 243.0 * (n - 2) ** 3
-            achieved = b_alg * apps / sec / 1e9
-            name = {0: "k_spmv_dot_imp<8>", 1: "k_spmv_dot_tile", 2: "k_spmv_dot_tma", 3: "k_spmv_dot_tmac"}[implicit_kernel]
-            key = "implicit_" + {0: "simple", 1: "tile", 2: "tma", 3: "tmac"}[implicit_kernel]
-            r = {"kernel": name + " (DPCG SpMV + p.Ap on the implicit elastic operator: no matrix stream)",
-                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                 "peak_source": peak_src, "traffic": None, "bytes_per_rve_application": b_alg,
-                 "limiter": "fp64 pipe, not HBM: the 1944 B/node matrix stream of the assembled path is eliminated, "
-                            "not moved faster (see roofline_assembled for the HBM-bound SpMV of the same workload)",
-                 "fp64": {"achieved_tflops": flops * apps / sec / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
-                          "frac": flops * apps / sec / 1e12 / FP64_PEAK_TFLOPS,
-                          "peak_source": "nominal: 148 SM x 64 DFMA/clk x 1965 MHz"},
-                 "equivalent_664": 664.0 * 3 * n ** 3 * apps / sec / 1e9}
-        else:
-            b_alg, b_664 = spmv_bytes_per_rve(n)
-            achieved = b_alg * apps / sec / 1e9
-            key = "assembled"
-            r = {"kernel": "k_spmv_dot (DPCG SpMV + p.Ap, one assembled ELL matrix per RVE)", "bound": "hbm",
-                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                 "traffic": None, "achieved_664": b_664 * apps / sec / 1e9, "bytes_per_rve_application": b_alg}
-        # the DPCG vector kernels (cg_update + cg_pupdate, HBM-bound streams; cg_init / cg_finish / u += du are in the
-        # same timer but run once per Newton step): bytes per node and iteration from DESIGN.md section 5
-        vec_b = (76.0 + 124.0 if implicit_kernel >= 0 else 120.0 + 120.0) * n ** 3
-        vec_sec = max(prof["cg_vec_ms"], 1e-9) * 1e-3
-        common["dpcg_vector_kernels"] = {"bound": "hbm", "achieved": vec_b * apps / vec_sec / 1e9, "peak": peak,
-                                         "unit": "GB/s", "frac": vec_b * apps / vec_sec / 1e9 / peak,
-                                         "bytes_per_rve_iteration": vec_b,
-                                         "share_of_step": prof["cg_vec_ms"] / max(prof_ms, 1e-9)}
-        r.update(common)
-        tr = ROOT / "profiles" / "spmv_traffic.json"  # dram bytes per RVE application from the committed ncu captures
-        if tr.exists():
+    # ---------------------------------------------------------------- the other BASELINE configs, bounded
+    if not args.no_extra and not args.full_path:
+        extras = {}
+        for x in [t for t in args.extra.split(",") if t and t != name]:
+            t0 = time.perf_counter()
             try:
-                per_rve = json.loads(tr.read_text())[args.workload][key]["dram_bytes_per_rve_application"]
-                r["traffic"] = per_rve * apps / max(prof["spmv_launches"], 1)  # per launch, like `achieved`
-                r["algorithmic_bytes_per_launch"] = b_alg * apps / max(prof["spmv_launches"], 1)
-            except Exception:
-                pass
-        return r
+                if x == "slab200":
+                    extras[x] = run_slab(M, env, args.slab_n, 2)
+                elif x in WORKLOADS:
+                    extras[x] = run_b200_workload(M, env, x, EXTRA_NGP[x], 2, 3, cpu_baseline=not args.no_cpu_baseline,
+                                                  cpu_sample=None, assembled_repeat=False)
+                    extras[x].update(metric=METRIC, higher_is_better=True, scaling="weak", n_gpus=world)
+            except Exception as ex:   # an extra workload never takes the headline down
+                extras[x] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+            extras[x]["bench_wall_s"] = time.perf_counter() - t0
+        line["workloads"] = extras
 
-    roof = spmv_roofline(prof, prof_dev_ms, apps, imp_kernel, steps)
-
-    # all-elastic workloads: the same workload once more through the assembled-matrix path (MICROPP_IMPLICIT=0) on a
-    # bounded batch, instrumented, so that the HBM-bound SpMV the north star names is measured in the same run
-    roof_asm = None
-    if imp_kernel >= 0 and rank == 0 and not args.no_assembled:
-        try:
-            ngp_a = min(ngp, 256)
-            os.environ["MICROPP_IMPLICIT"] = "0"
-            ma = M.Micropp3(M.default_params(size=(n, n, n), ngp=ngp_a, mpi_rank=local_rank, **wl["params"]))
-            del os.environ["MICROPP_IMPLICIT"]
-            ea = strains_for(args.workload, ngp, rank, kk)[:ngp_a]
-            ma.set_strains(ea)
-            for _ in range(2):
-                ma.homogenize()
-            ma.prof_enable(True)
-            ma.prof_read(True)
-            ma.homogenize()
-            ms_a = ma.last_homogenize_ms()
-            prof_a = ma.prof_read(True)
-            ma.prof_enable(False)
-            apps_a = float(sum(ma.get_cost(g) for g in range(ngp_a)))
-            roof_asm = spmv_roofline(prof_a, ms_a, apps_a, -1, 1)
-            roof_asm["gps"] = ngp_a
-            roof_asm["value_gps_per_s"] = ngp_a / (ms_a * 1e-3)
-            sa = ma.get_stresses()
-            roof_asm["max_rel_diff_vs_implicit"] = float(np.max(np.abs(sa - sig_h[:ngp_a]) /
-                                                                np.max(np.abs(sa), axis=1, keepdims=True)))
-            ma.close()
-        except Exception as ex:
-            os.environ.pop("MICROPP_IMPLICIT", None)
-            roof_asm = {"unavailable": str(ex)}
-
-    line = {"metric": "homogenized GPs/sec (DPCG+assembly)", "value": total_gps * steps / (dev_ms_max * 1e-3),
-            "unit": "GP/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms_max / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(base_cfg, newton_cg={"mean_cg_its_per_gp": float(np.mean(cost)), "converged": conv,
-                                                 "non_linear_gps": nl, "wave": m.wave_size()},
-                           ctor_s=ctor_s),
-            "e2e": {"value": total_gps * steps / wall2_max, "unit": "GP/s", "h2d_bytes_per_step": int(ngp * 48),
-                    "d2h_bytes_per_step": int(ngp * 48), "ms_per_step": wall2_max / steps * 1e3},
-            "gpu_launches": launches_tot, "clocks": clocks, "roofline": roof}
-    if roof_asm is not None:
-        line["roofline_assembled"] = roof_asm
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cores = host_cores()
-            sample = args.cpu_sample or (4 * cores if args.workload == "elastic30" else cores)
-            res = run_reference(args, wl, sample, 1, 0)
-            line["cpu_baseline"] = {"value": res["value"], "unit": "GP/s", "cores": res["cores"],
-                                    "kind": "reference", "sample": res["sample"]}
-        except Exception as ex:  # the baseline is reported, never required for the GPU number
-            line["cpu_baseline"] = {"value": None, "unit": "GP/s", "cores": host_cores(), "kind": "reference",
-                                    "sample": f"unavailable: {ex}"}
-    m.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -314,7 +314,7 @@ def test_fe_full_ctan_values(mpp, refpy):
                 assert relerr(a["sig"][gp], b["sig"][gp]) < 1e-10, (case, k, gp)
                 worst = max(worst, relerr(a["ctan"][gp], b["ctan"][gp]))
         print(f"FE_FULL ctan {case}: worst relative difference to the reference {worst:.3e}")
-        assert worst < 1e-6, (case, worst)
+        assert worst < 1e-8, (case, worst)   # measured on the B200: 1.2e-9 (damage), 1.0e-9 (plastic)
         # the tangent really is the non-linear one (differs from the linear ctan of the constructor)
         assert relerr(hg[-1]["ctan"][0], g.ctan_lin()) > 1e-3
 
