@@ -113,16 +113,16 @@ void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_share
    of the last mgpu_cg_init */
 /* host-only (no GPU): tiling of the implicit operator's TMA kernel for an nx x ny x nz RVE; see mgpu_kernels.cu */
 int mgpu_tmac_tiling_host(int nx, int ny, int nz, const int *elem_type, int *meta6, int *rowid, int *tiles4,
-                          int *chunk_pure, int *fix_ptr, int *tasks4);
+                          int *chunk_pure, int *fix_nodes2);
 int mgpu_implicit(const mgpu_ctx *);
 int mgpu_implicit_rows(const mgpu_ctx *);     /* distinct ELL row blocks of the implicit operator */
-int mgpu_implicit_fix_nodes(const mgpu_ctx *); /* interior nodes on material interfaces (fix-up list of the TMA kernel) */
-int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 simple, 1 tiled (cp.async), 2 tiled (TMA, rows in smem), 3 tiled (TMA, rows as kernel parameter: k_spmv_dot_tmac) */
+int mgpu_implicit_fix_nodes(const mgpu_ctx *); /* interior nodes served by k_spmv_fix (material interfaces + minority nodes of a chunk) */
+int mgpu_implicit_kernel(const mgpu_ctx *);   /* -1 none; SpMV kernel of the implicit operator: 0 k_spmv_dot_imp (table-driven; odd nx), 3 k_spmv_dot_tmac (TMA load + TMA store) + k_spmv_fix */
 void mgpu_cg_init(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_cg_spmv_dot(mgpu_ctx *, int which_list, int n, int use_shared);
 void mgpu_spmv_generic(mgpu_ctx *, int which_list, int n, int force); /* arbitrary matrix: boundary rows read too */
 /* one forced application Ap = A p (+ p.Ap in the slot state) for kernel parity tests; op as in mgpu_cg_init;
-   imp_kernel: -1 the context's choice, 0 the simple multi-right-hand-side kernel, 1 the shared-memory tiled kernel */
+   imp_kernel: -1 the context's choice, 0 k_spmv_dot_imp, 3 k_spmv_dot_tmac + k_spmv_fix */
 void mgpu_apply_operator(mgpu_ctx *, int which_list, int n, int op, int imp_kernel);
 void mgpu_cg_update(mgpu_ctx *, int which_list, int n);
 void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
@@ -160,6 +160,9 @@ void mgpu_slab_publish_p(mgpu_ctx *);
 void mgpu_slab_halo_pull(mgpu_ctx *);
 void mgpu_slab_post(mgpu_ctx *, int k);
 void mgpu_slab_gather_tail(mgpu_ctx *, int which_list, int k, int kind, int mode); /* kind / mode as mgpu_tail */
+/* fused path (one launch per cross-rank reduction: fold + post + gather + tail; the p update publishes its epoch) */
+void mgpu_slab_set_fused(mgpu_ctx *, int on);
+void mgpu_slab_reduce_tail(mgpu_ctx *, int which_list, int k, int kind, int mode);
 int mgpu_slab_error(mgpu_ctx *);  /* != 0: a wait for a peer timed out (syncs) */
 void mgpu_slab_cg_iteration(mgpu_ctx *, int which_list, int op);
 void mgpu_slab_cg_chunk(mgpu_ctx *, int which_list, int op, int iters); /* iters iterations as one CUDA graph launch */
@@ -193,7 +196,7 @@ void mgpu_timer_start(mgpu_ctx *);
 float mgpu_timer_stop(mgpu_ctx *); /* ms on the context stream (syncs) */
 /* isolated SpMV micro-benchmark on the first n slots of the pool (matrix contents as they are) */
 float mgpu_bench_spmv(mgpu_ctx *, int n, int iters);
-/* same for the implicit elastic operator; kern as in mgpu_apply_operator (2 = context default, 10 + v = TMA variant v) */
+/* same for the implicit elastic operator; kern as in mgpu_apply_operator */
 float mgpu_bench_imp_spmv(mgpu_ctx *, int n, int iters, int kern);
 
 #ifdef __cplusplus

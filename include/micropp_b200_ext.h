@@ -52,7 +52,7 @@ int micropp3x_nndim(const struct micropp3 *self);
 int micropp3x_wave_size(const struct micropp3 *self);
 /* distinct ELL row blocks of the implicit operator of an all-elastic RVE; 0 = one assembled matrix per slot */
 int micropp3x_implicit_rows(const struct micropp3 *self);
-/* -1: assembled matrices; else the implicit SpMV kernel in use: 0 simple, 1 tiled (cp.async), 2 tiled (TMA) */
+/* -1: assembled matrices; else the implicit SpMV kernel in use: 0 k_spmv_dot_imp (odd nx), 3 k_spmv_dot_tmac */
 int micropp3x_implicit_kernel(const struct micropp3 *self);
 void micropp3x_get_elem_type(const struct micropp3 *self, int *out);
 void micropp3x_get_bmat(const struct micropp3 *self, double *out /* [8][6][24] */);
@@ -69,7 +69,7 @@ void micropp3x_ave_stress(struct micropp3 *self, const double *u, const double *
 int micropp3x_vars_new(struct micropp3 *self, const double *u, const double *vars_old, double *vars_new);
 /* Ap = A p with the Jacobian at u = 0 without history (ell_mvp of src/ell.cpp:35-44 on the matrix assembly_mat
    builds), through the chosen DPCG operator: op 0 = assembled ELL matrix, 3 = implicit operator of an all-elastic
-   RVE (kernel 0 simple / 1 tiled / -1 default).  p, Ap in the reference's layout [node][3]; returns p.Ap */
+   RVE (kernel 0 table-driven / 3 TMA-tiled / -1 default).  p, Ap in the reference's layout [node][3]; returns p.Ap */
 double micropp3x_apply_operator(struct micropp3 *self, const double *p, double *Ap, int op, int kernel);
 
 /* ELL pieces */
@@ -85,13 +85,41 @@ int micropp3x_elem_colour(int ex, int ey, int ez);
    neighbour.  Returns an `mgpu_ctx *` (include/mgpu.h) that the caller drives; see micropp_b200/slab.py. */
 struct mgpu_ctx *micropp3x_slab_create(const struct micropp3_params *params, int z0, int z1, int device);
 
+/* ---- z-slab mode behind the C ABI (host logic in micropp_b200/csrc/slab_host.cpp) --------------------------------
+   One rank per GPU:  s = micropp3x_slab_new(&params, rank, size, device);  micropp3x_slab_export(s, &mine);
+   all-gather the handles with whatever the macro code has (MPI_Allgather of bytes; torch.distributed in bench.py);
+   micropp3x_slab_connect(s, all);  then every rank calls micropp3x_slab_homogenize(s, eps, sig, out3) -- inside a solve
+   the ranks exchange halo planes and dot products over NVLink peer memory only (device-side flags, no collective).
+   out3 = {Newton iterations, DPCG iterations, converged}.  Returns 0, or < 0 on misuse / a lost peer. */
+struct micropp3x_slab;
+struct micropp3x_slab_handle {
+  char mail[64];      /* CUDA IPC handle of this rank's mailbox */
+  char p[64];         /* CUDA IPC handle of this rank's search-direction vector */
+  long long nzl;      /* local node planes (halo planes included) */
+  long long nn_pad;   /* component stride of the local vectors */
+  int op, pad;        /* DPCG operator this rank would choose alone (3 implicit, 0 assembled) */
+};
+struct micropp3x_slab *micropp3x_slab_new(const struct micropp3_params *params, int rank, int size, int device);
+void micropp3x_slab_free(struct micropp3x_slab *);
+void micropp3x_slab_export(struct micropp3x_slab *, struct micropp3x_slab_handle *mine);
+void micropp3x_slab_connect(struct micropp3x_slab *, const struct micropp3x_slab_handle *all /* [size] */);
+int micropp3x_slab_homogenize(struct micropp3x_slab *, const double *eps6, double *stress6, int *out3);
+/* several slabs of one RVE in ONE process / on one GPU (tests): plain device pointers instead of IPC handles */
+void micropp3x_slab_connect_local(struct micropp3x_slab *const *group, int n);
+int micropp3x_slab_homogenize_local(struct micropp3x_slab *const *group, int n, const double *eps6, double *stress6,
+                                    int *out3);
+void micropp3x_slab_planes(const struct micropp3x_slab *, int *z0, int *z1); /* owned node planes [z0, z1) */
+void micropp3x_slab_get_u(struct micropp3x_slab *, double *u_local /* [nzl*ny*nx][3] */);
+unsigned long long micropp3x_slab_launch_count(const struct micropp3x_slab *);
+int micropp3x_slab_operator(const struct micropp3x_slab *);
+
 /* measurement (CUDA events on the library's own stream) */
 void micropp3x_prof_enable(struct micropp3 *self, int on);
 void micropp3x_prof_read(struct micropp3 *self, double *out6, int reset);
 double micropp3x_last_homogenize_ms(const struct micropp3 *self);
 unsigned long long micropp3x_launch_count(const struct micropp3 *self);
 double micropp3x_bench_spmv(struct micropp3 *self, int nslots, int iters); /* ms per launch */
-/* implicit elastic operator; kern: 2 = the context's kernel, 10 + v = TMA variant v (0 shared-memory rows, v >= 1 kernel-parameter rows) */
+/* implicit elastic operator; kern: -1 the context's kernel, 0 k_spmv_dot_imp, 3 k_spmv_dot_tmac + k_spmv_fix */
 double micropp3x_bench_imp_spmv(struct micropp3 *self, int nslots, int iters, int kern);
 
 #ifdef __cplusplus

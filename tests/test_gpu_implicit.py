@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 
 def run(mod_cls, params, eps, implicit=None, kernel=None):
     """One homogenize() of a fresh object; implicit / kernel select the operator through the environment
-    (MICROPP_IMPLICIT: 0 = one assembled ELL matrix per slot; MICROPP_IMP_KERNEL: 0 = simple multi-RHS kernel,
-    1 = shared-memory tiled kernel, the default)."""
+    (MICROPP_IMPLICIT: 0 = one assembled ELL matrix per slot; MICROPP_IMP_KERNEL: 0 = k_spmv_dot_imp, the table-driven
+    multi-RHS kernel; unset = the default: k_spmv_dot_tmac + k_spmv_fix (TMA load and TMA store) when nx is even)."""
     env = {}
     if implicit is not None:
         env["MICROPP_IMPLICIT"] = "1" if implicit else "0"
@@ -57,12 +57,12 @@ def test_implicit_simple_kernel_equals_explicit_bitwise(mpp, dims, ngp):
         assert np.array_equal(gi.get_u(gp), ge.get_u(gp))
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
-@pytest.mark.parametrize("dims,ngp", DIMS + [((16, 16, 16), 9), ((20, 10, 12), 2)])
-def test_implicit_tiled_kernels_equal_explicit(mpp, dims, ngp, kernel):
-    """kernel 1 = shared-memory tiles filled by cp.async, 2 = by TMA (even nx; silently 1 otherwise).  Ap is
-    bit-identical (test_operator_application), p.Ap is summed in another fixed order, so the DPCG path differs by
-    rounding.  DPCG stops at |z| < 1e-5 |z0| and amplifies rounding differences by about 1/tolerance x condition:
+@pytest.mark.parametrize("kernel", [None])
+@pytest.mark.parametrize("dims,ngp", DIMS + [((16, 16, 16), 9), ((20, 10, 12), 2), ((30, 30, 30), 3), ((40, 18, 70), 2)])
+def test_implicit_tma_kernels_equal_explicit(mpp, dims, ngp, kernel):
+    """The default kernels (k_spmv_dot_tmac + k_spmv_fix when nx is even, else the table-driven kernel -- said on
+    stderr).  Ap is bit-identical (test_operator_application), p.Ap is summed in another fixed order, so the DPCG path
+    differs by rounding.  DPCG stops at |z| < 1e-5 |z0| and amplifies rounding differences by about 1/tolerance x condition:
     cubic meshes stay below 1e-9, strongly anisotropic ones (dx != dy != dz) reach 1e-7 -- the same size as the
     difference between the assembled-matrix path and the reference CPU path on those meshes."""
     rng = np.random.default_rng(43)
@@ -132,6 +132,7 @@ def test_operator_application_three_ways(mpp, refpy, dims):
     p = p.reshape(-1)
     y0, d0 = g.apply_operator(p, op=0)
     y1, d1 = g.apply_operator(p, op=3, kernel=0)
+    assert g.implicit_kernel() == (3 if nx % 2 == 0 else 0)   # k_spmv_dot_tmac whenever TMA can address the rows
     bad = np.nonzero(y0 != y1)[0]
     if bad.size:   # diagnostics: which of the two is unstable, and which agrees with the reference
         y0b, _ = g.apply_operator(p, op=0)
@@ -144,15 +145,15 @@ def test_operator_application_three_ways(mpp, refpy, dims):
                                   err_y0=relerr(y0[inner], yr[inner]), err_y1=relerr(y1[inner], yr[inner]),
                                   err_y0b=relerr(y0b[inner], yr[inner])))
     assert d0 == d1
-    # 1 = cp.async tiles, 2 = the context's TMA kernel, 10 = k_spmv_dot_tma (row blocks in shared memory, 8 nodes per
-    # thread), 11..13 = the k_spmv_dot_tmac variants (row blocks as a kernel parameter, 7 or 8 nodes per thread, tile
-    # descriptors with two lane shapes; 2 stages / 1 stage x 3 blocks per SM / 1 stage x 4 blocks per SM)
-    for kernel in (1, 2, 10, 11, 12, 13, 14):
-        y2, d2 = g.apply_operator(p, op=3, kernel=kernel)
-        assert np.array_equal(y0, y2), kernel
-        assert abs(d2 - d0) <= 1e-13 * abs(d0), kernel
+    inner = ~np.repeat(bnd, 3)
+    # 3 = k_spmv_dot_tmac (TMA load, TMA store) + k_spmv_fix: all 243 terms per node in the reference's order -- the
+    # same bits as the assembled path, also at the nodes whose tile store writes a zero first (k_spmv_fix overwrites it)
+    y2, d2 = g.apply_operator(p, op=3, kernel=3)
+    assert np.array_equal(y0, y2)
+    assert abs(d2 - d0) <= 1e-13 * abs(d0)
+    y2b, d2b = g.apply_operator(p, op=3, kernel=3)
+    assert np.array_equal(y2, y2b) and d2 == d2b          # deterministic
     r = refpy.RefMicropp(refpy.default_params(**kw))
     A = r.assembly_mat(np.zeros(g.nndim))
     yr = refpy.ell_mvp(*dims, A, p)
-    inner = ~np.repeat(bnd, 3)
     assert relerr(y0[inner], yr[inner]) < 1e-13

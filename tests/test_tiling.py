@@ -1,7 +1,8 @@
 """CPU: the tiling of the implicit operator's TMA kernel (k_spmv_dot_tmac) as the HOST builds it -- tile descriptors
-with two lane shapes, 7 or 8 nodes per thread, the pure row block + fix-up mask of every chunk, the fix-up tasks --
-replayed with the kernel's own ownership rules: every interior node must be produced exactly once, with the row block
-the node really has, and every shared-memory index must stay inside the brick.  (The GPU tests check bit-identity of
+with two lane shapes, 7 or 8 nodes per thread, the pure row block + keep mask of every chunk, the list of nodes that
+k_spmv_fix serves -- replayed with the kernels' own ownership rules: every interior node must be produced exactly once,
+with the row block the node really has; every shared-memory index must stay inside the brick; the Ap box of a tile
+(TMA store) must be a 16-byte multiple wide, fit in the brick's memory and never reach another tile's nodes.  (The GPU tests check bit-identity of
 the operator on about 20 shapes; this covers the bench sizes, 200^3 and odd shapes without a GPU.)"""
 import ctypes as C
 
@@ -32,22 +33,20 @@ def tiling(lib, dims, et):
     ip = C.POINTER(C.c_int)
     f = lib.mgpu_tmac_tiling_host
     f.restype = C.c_int
-    f.argtypes = [C.c_int] * 3 + [ip] * 7
+    f.argtypes = [C.c_int] * 3 + [ip] * 6
     meta = np.zeros(6, dtype=np.int32)
     et = np.ascontiguousarray(et, dtype=np.int32)
-    nrows = f(nx, ny, nz, et.ctypes.data_as(ip), meta.ctypes.data_as(ip), None, None, None, None, None)
-    tn, cb, nchunk, pitch, ntiles, ntasks = (int(v) for v in meta)
+    nrows = f(nx, ny, nz, et.ctypes.data_as(ip), meta.ctypes.data_as(ip), None, None, None, None)
+    tn, cb, nchunk, pitch, ntiles, nfix = (int(v) for v in meta)
     nix, niy, niz = nx - 2, ny - 2, nz - 2
     rowid = np.zeros(nix * niy * niz, dtype=np.int32)
     tiles = np.zeros((ntiles, 4), dtype=np.int32)
     pure = np.zeros(niz * niy * nchunk, dtype=np.int32)
-    fptr = np.zeros(ntiles + 1, dtype=np.int32)
-    tasks = np.zeros((max(ntasks, 1), 4), dtype=np.int32)
+    fix = np.zeros((max(nfix, 1), 2), dtype=np.int32)
     f(nx, ny, nz, et.ctypes.data_as(ip), meta.ctypes.data_as(ip), rowid.ctypes.data_as(ip), tiles.ctypes.data_as(ip),
-      pure.ctypes.data_as(ip), fptr.ctypes.data_as(ip), tasks.ctypes.data_as(ip))
-    return dict(tn=tn, cb=cb, nchunk=nchunk, pitch=pitch, ntiles=ntiles, ntasks=ntasks, nrows=nrows,
-                rowid=rowid.reshape(niz, niy, nix), tiles=tiles, pure=pure.reshape(niz, niy, nchunk), fptr=fptr,
-                tasks=tasks[:ntasks])
+      pure.ctypes.data_as(ip), fix.ctypes.data_as(ip))
+    return dict(tn=tn, cb=cb, nchunk=nchunk, pitch=pitch, ntiles=ntiles, nfix=nfix, nrows=nrows,
+                rowid=rowid.reshape(niz, niy, nix), tiles=tiles, pure=pure.reshape(niz, niy, nchunk), fix=fix[:nfix])
 
 
 @pytest.mark.parametrize("dims,kind", [((30, 30, 30), "sphere"), ((50, 50, 50), "sphere"), ((40, 40, 40), "layer"),
@@ -63,6 +62,8 @@ def test_tmac_tiling_covers_every_interior_node_once(dims, kind):
     nix, niy, niz = nx - 2, ny - 2, nz - 2
     tn, cb, pitch = t["tn"], t["cb"], t["pitch"]
     assert tn in (7, 8) and 1 <= cb <= 4 and t["nchunk"] == -(-nix // tn)
+    pxo = tn * cb - 2                                # the Ap box of a tile: its middle nodes (16-B aligned TMA origin)
+    assert pxo % 2 == 0 and pxo >= 2 and 3 * 32 * pxo <= 3 * 60 * pitch
     assert pitch % 2 == 0 and (pitch // 2) % 2 == 1 and pitch >= tn * cb + 2      # 16-B rows, conflict-free quarter-warps
     assert t["nrows"] >= 3 and t["rowid"].max() < t["nrows"]
     count = np.zeros((niz, niy, nix), dtype=np.int32)
@@ -90,25 +91,32 @@ def test_tmac_tiling_covers_every_interior_node_once(dims, kind):
                 assert np.all(node_ids[sel] == (info & 0xff)[sel])                     # kept nodes use the chunk's pure block
                 count[np.ix_(kk, jj, [c * tn + tt])][:, :, 0]                          # (bounds check of the index)
                 count[kk[:, None], jj[None, :], c * tn + tt] += sel
-        for e in t["tasks"][t["fptr"][tile]:t["fptr"][tile + 1]]:
-            for pos in (int(e[0]), int(e[1])):
-                if pos < 0:
-                    continue
-                lx, fy, fz = pos & 0xff, (pos >> 8) & 0xf, (pos >> 12) & 0xf
-                assert fy < ny_t and fz < nz_t and lx < tn * cb
-                assert lx + xoff + 2 < pitch and fy + 2 < by and fz + 2 < bz           # neighbours inside the brick
-                x, y, z = c0 * tn + lx, y0 + fy, z0 + fz
-                assert t["rowid"][z, y, x] == int(e[2])                                # the task's row block is the node's
-                count[z, y, x] += 1
+    # tiles partition the chunk grid: no chunk is served twice, so the Ap boxes (which may only overhang the interior at
+    # its high ends, where they meet boundary nodes or leave the grid) never touch another tile's nodes
+    owner = np.zeros((niz, niy, t["nchunk"]), dtype=np.int32)
+    for tile in range(t["ntiles"]):
+        c0, y0, z0, shape = (int(v) for v in t["tiles"][tile])
+        ny_t, nz_t = (TILE_Z, TILE_Y) if shape else (TILE_Y, TILE_Z)
+        owner[z0:z0 + nz_t, y0:y0 + ny_t, c0:c0 + cb] += 1
+    assert owner.min() == 1 and owner.max() == 1
+    # the nodes no chunk keeps go to k_spmv_fix with their own row block
+    for node, rid in t["fix"]:
+        k, rem = divmod(int(node), nx * ny)
+        j, i = divmod(rem, nx)
+        assert 1 <= i <= nix and 1 <= j <= niy and 1 <= k <= niz
+        assert rid == t["rowid"][k - 1, j - 1, i - 1]
+        count[k - 1, j - 1, i - 1] += 1
     assert count.min() == 1 and count.max() == 1
-    # interface nodes = nodes whose 8 elements are not all of one material
-    assert t["fptr"][-1] == t["ntasks"]
+    assert t["nfix"] >= int(np.sum(t["rowid"] >= 3))       # interface nodes + minority nodes of a chunk
+    if kind == "sphere" and min(dims) >= 24:
+        assert t["nfix"] < 0.08 * nix * niy * niz
 
 
 def test_tmac_tiling_efficiency_at_bench_sizes():
-    """Executed node slots per interior node: 30^3 -> 22400 / 21952 (7 nodes per thread + a 4y x 8z strip), 50^3 exact."""
+    """Executed node slots per interior node: 30^3 -> 22400 / 21952 (7 nodes per thread + a 4y x 8z strip), 50^3 exact;
+    40^3 pays for the even-width Ap box (7 nodes per thread only with 2 or 4 warps): 8 nodes x 3 warps, 48 slots for 38."""
     lib = M.load()
-    for n, bound in ((30, 1.03), (50, 1.0001), (40, 1.25), (200, 1.12)):
+    for n, bound in ((30, 1.03), (50, 1.0001), (40, 1.42), (200, 1.12)):
         dims = (n, n, 12 if n == 200 else n)
         t = tiling(lib, dims, sphere_types(*dims))
         executed = t["ntiles"] * t["cb"] * 32 * t["tn"]

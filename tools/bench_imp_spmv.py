@@ -1,10 +1,11 @@
-"""Isolated timing of the implicit elastic SpMV variants (k_spmv_dot_tma / k_spmv_dot_tmac) on one B200.
+"""Isolated timing of the implicit elastic SpMV kernels on one B200.
 
-    python tools/bench_imp_spmv.py [n=30] [ngp=1024] [iters=20]
+    python tools/bench_imp_spmv.py [n=30] [ngp=1024] [iters=20] [case=elastic_sphere|homog]
 
-Prints ms per application of the operator to `ngp` RVEs, FP64 TFLOP/s (2*243 flop per interior node) and the
-fraction of the nominal FP64 peak (148 SM x 64 DFMA/clk x 1965 MHz = 37.2 TFLOP/s) for every variant, after checking
-that every variant returns the bits of the simple kernel on a random vector.
+Prints ms per application of the operator to `ngp` RVEs (SpMV + its p.Ap fold), FP64 TFLOP/s counted with the
+ALGORITHMIC 2*243 flop per interior node, and the fraction of the nominal FP64 peak (148 SM x 64 DFMA/clk x 1965 MHz
+= 37.2 TFLOP/s), for k_spmv_dot_imp (0) and k_spmv_dot_tmac + k_spmv_fix (3), after comparing them on a random vector
+(same bits).
 """
 import json
 import os
@@ -31,28 +32,26 @@ p = rng.uniform(-1, 1, m.nndim)
 y0, d0 = m.apply_operator(p, op=3, kernel=0)
 flop = 2.0 * 243 * (n - 2) ** 3 * ngp
 peak = 148 * 64 * 2 * 1.965e9
-names = {0: "k_spmv_dot_tma (rows in smem, 8 nodes/thread, 2 stages, 2 blocks/SM)",
-         1: "k_spmv_dot_tmac 2 stages, 2 blocks/SM, unroll 1", 2: "k_spmv_dot_tmac 1 stage, 3 blocks/SM, unroll 1",
-         3: "k_spmv_dot_tmac 1 stage, 4 blocks/SM, unroll 1", 4: "k_spmv_dot_tmac 2 stages, 2 blocks/SM, unroll 3"}
+names = {0: "k_spmv_dot_imp (table-driven, 8 slots per thread)",
+         3: "k_spmv_dot_tmac + k_spmv_fix (TMA load + TMA store per tile; interface nodes by the table-driven kernel)"}
 from bench import ClockSampler
-only = [int(x) for x in os.environ.get("VARIANTS", "0,1,2,3,4").split(",")]
-long_iters = int(os.environ.get("LONG_ITERS", "0"))   # > 0: one long run per variant with nvidia-smi clock sampling
+only = [int(x) for x in os.environ.get("KERNELS", "0,3").split(",")]
+long_iters = int(os.environ.get("LONG_ITERS", "0"))   # > 0: one long run per kernel with nvidia-smi clock sampling
 out = []
 for v in only:
-    y, d = m.apply_operator(p, op=3, kernel=10 + v)
-    same = bool(np.array_equal(y, y0))
-    ms = min(m.bench_imp_spmv(ngp, iters, 10 + v) for _ in range(3))
+    y, d = m.apply_operator(p, op=3, kernel=v)
+    err = float(np.max(np.abs(y - y0)) / np.max(np.abs(y0)))
+    ms = min(m.bench_imp_spmv(ngp, iters, v) for _ in range(3))
     clk = None
     if long_iters:
         cs = ClockSampler(0)
         cs.start()
-        ms = m.bench_imp_spmv(ngp, long_iters, 10 + v)
+        ms = m.bench_imp_spmv(ngp, long_iters, v)
         clk = cs.stop()
     tf = flop / (ms * 1e-3) / 1e12
-    if v >= 1 and os.environ.get("SPLIT"):
-        t_nocompute = min(m.bench_imp_spmv(ngp, iters, 110 + v) for _ in range(2))
-        t_noload = min(m.bench_imp_spmv(ngp, iters, 210 + v) for _ in range(2))
-        print(f"   variant {v}: loads + stores only {t_nocompute:.3f} ms; compute on a stale brick only {t_noload:.3f} ms", flush=True)
-    out.append(dict(variant=v, name=names[v], ms=ms, tflops=tf, frac_fp64_peak=tf * 1e12 / peak, bit_identical=same, clocks=clk))
-    print(f"variant {v}: {ms:8.3f} ms  {tf:6.2f} TFLOP/s  {tf*1e12/peak:5.1%} of FP64 peak  bits_ok={same}  {names[v]}  clocks={clk}", flush=True)
-print(json.dumps({"case": case, "fix_nodes": m.lib.micropp3x_implicit_rows(__import__("ctypes").byref(m.h)), "rve": n, "ngp": ngp, "iters": iters, "variants": out}))
+    out.append(dict(kernel=v, name=names[v], ms=ms, tflops=tf, frac_fp64_peak=tf * 1e12 / peak, relerr_vs_table=err,
+                    dot_relerr=abs(d - d0) / abs(d0), clocks=clk))
+    print(f"kernel {v}: {ms:8.3f} ms  {tf:6.2f} TFLOP/s  {tf*1e12/peak:5.1%} of FP64 peak  err={err:.1e}  {names[v]}  "
+          f"clocks={clk}", flush=True)
+print(json.dumps({"case": case, "implicit_kernel": m.implicit_kernel(),
+                  "rve": n, "ngp": ngp, "iters": iters, "kernels": out}))
