@@ -666,15 +666,23 @@ __global__ void __launch_bounds__(NT, 4)
   }
 }
 
-// `publish` (slab mode over peer memory, fused path): the LAST block to finish -- ticket in the mailbox -- publishes the
-// epoch of this p update, so the neighbours' halo pull needs no extra launch.  Every block takes a ticket, also when
-// the slot has already left the loop (all ranks run the same launch sequence).
-__device__ __forceinline__ void slab_publish_after_update(SlabMail *mail) {
+// `publish` (slab mode over peer memory, fused path): the LAST of the blocks that write a halo-relevant plane -- ticket in
+// the mailbox -- publishes the epoch of this p update, so the neighbours' halo pull needs no extra launch.  The
+// tickets are taken also when the slot has already left the loop (all ranks run the same launch sequence).
+__device__ __forceinline__ void slab_publish_after_update(const MeshConst &P, SlabMail *mail) {
+  // only the blocks that write the two planes a neighbour pulls (the bottom and top OWNED planes: local planes 1 and
+  // nz - 2) take part: a system-scope fence + ticket in all 62 500 blocks of a 200^3 slab costs more than the update
+  const int lo1 = P.nxny / NT, hi1 = (2 * P.nxny - 1) / NT;
+  const int lo2 = ((P.nz - 2) * P.nxny) / NT, hi2 = ((P.nz - 1) * P.nxny - 1) / NT;
+  const int b = blockIdx.x;
+  if (!((b >= lo1 && b <= hi1) || (b >= lo2 && b <= hi2))) return;
+  const int overlap = max(0, min(hi1, hi2) - max(lo1, lo2) + 1);
+  const unsigned expected = (unsigned)((hi1 - lo1 + 1) + (hi2 - lo2 + 1) - overlap) * gridDim.y;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(&mail->pub_ticket, 1u);
-    if (t == gridDim.x * gridDim.y - 1) {
+    if (t == expected - 1) {
       mail->pub_ticket = 0u;
       const unsigned long long epoch = ++mail->p_local;
       __threadfence_system();
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(NT)
       V.p[ix] = z + beta * pp;
     }
   }
-  if (publish) slab_publish_after_update(publish);
+  if (publish) slab_publish_after_update(P, publish);
 }
 
 // Arbitrary user matrix in the reference's own layout vals[row*81 + slot] (host-pointer ell_mvp / ell_solve_cgpd
@@ -815,7 +823,7 @@ __global__ void __launch_bounds__(NT)
       V.p[ix] = V.z[ix] + beta * pp;
     }
   }
-  if (publish) slab_publish_after_update(publish);
+  if (publish) slab_publish_after_update(P, publish);
 }
 
 // x += alpha p of the LAST iteration of every slot of the list that iterated at all: its p update was skipped because
@@ -1111,18 +1119,34 @@ __global__ void k_slab_gather_tail(const __grid_constant__ MeshConst P, const Ls
 // (kind 2: p.Ap partials of the SpMV; kind 3: z.z / r.z partials of the r update; other kinds: T.red as their ticket
 // reductions left it), posts them in the mailbox, waits for every rank's post, adds them in RANK ORDER and runs the
 // scalar tail -- what used to be k_fold_* + k_slab_post + k_slab_gather_tail, three launches per reduction.
+// sum of n partials by the whole block in a fixed order (strided per-thread sums, then a fixed tree): deterministic;
+// result valid in thread 0.  A 200^3 slab leaves tens of thousands of partials -- too many for one warp.
+__device__ __forceinline__ double block_fold(const double *partial, int n, double *sm /* [blockDim.x / 32] */) {
+  double acc = 0.0;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) acc += __ldcg(&partial[q]);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sm[w];
+  __syncthreads();
+  return tot;
+}
+
 __global__ void k_slab_reduce_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                                    const __grid_constant__ SlabPeers peers, SlabMail *own, int nranks, int k, int kind,
                                    int mode, int nfold) {
+  __shared__ double sm[32];
   const int slot = slot_of(L);
   if (slot < 0) return;
   double *red = T.red + slot * 8;
   if (kind == 2 && nfold > 0) {  // nfold == 0: the assembled SpMV's own ticket reduction already left p.Ap in T.red
-    const double s = fold_partials(T.partial + ((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max, nfold);
+    const double s = block_fold(T.partial + ((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max, nfold, sm);
     if (threadIdx.x == 0) red[0] = s;
   } else if (kind == 3) {
     const double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
-    const double zz = fold_partials(partial, nfold), rz = fold_partials(partial + T.nblk_max, nfold);
+    const double zz = block_fold(partial, nfold, sm), rz = block_fold(partial + T.nblk_max, nfold, sm);
     if (threadIdx.x == 0) {
       red[0] = zz;
       red[1] = rz;
@@ -2117,8 +2141,9 @@ void mgpu_slab_set_fused(mgpu_ctx *c, int on) { c->slab_fused = on != 0; }
 void mgpu_slab_reduce_tail(mgpu_ctx *c, int l, int k, int kind, int mode) {
   c->launches++;
   const int nfold = kind == 2 ? c->last_spmv_nfold : (kind == 3 ? c->last_update_nblk : 0);
-  k_slab_reduce_tail<<<dim3(1, 1), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
-                                                      c->slab_size, k, kind, mode, nfold);
+  const int threads = nfold > 4096 ? 1024 : (nfold > 256 ? 256 : 32);
+  k_slab_reduce_tail<<<dim3(1, 1), threads, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
+                                                           c->slab_size, k, kind, mode, nfold);
   CK(cudaGetLastError());
 }
 int mgpu_slab_error(mgpu_ctx *c) {

@@ -18,8 +18,13 @@ No other vector needs an exchange: x += alpha p keeps the halo entries of du (an
 halo entries of p are the neighbour's values and alpha is global.  Element layers that touch a cut are assembled by
 both sides; each layer is averaged by exactly one rank.
 
-`SlabRVE` can also hold several slabs in ONE process on one GPU (`world=None, nslabs=R`): the same code path with
-the exchange done by device copies -- used to test the decomposition on a single GPU.
+`SlabRVE` can also hold several slabs in ONE process on one GPU (`world=None, nslabs=R`): the same kernels with plain
+device pointers -- used to test the decomposition on a single GPU.
+
+Host logic: the product path (`exchange="peer"`) is C++ -- micropp_b200/csrc/slab_host.cpp behind the C ABI
+`micropp3x_slab_*` of include/micropp_b200_ext.h; this module only exchanges the CUDA IPC handles through the process
+group (a C++ macro code would use MPI_Allgather) and forwards the calls.  `exchange="nccl"` keeps a Python-driven loop
+over the same kernels with torch.distributed send/recv + all-reduce as the BASELINE transport it is measured against.
 """
 from __future__ import annotations
 
@@ -144,8 +149,10 @@ class _Slab:
             self.ctx = None
 
 
-class SlabRVE:
-    """One RVE, FE_ONE_WAY without history (elastic, or the first load step of any law), solved over z-slabs.
+class SlabRVEPy:
+    """PYTHON-DRIVEN variant (the NCCL baseline transport and the unfused peer kernels; see SlabRVE for the product path).
+
+    One RVE, FE_ONE_WAY without history (elastic, or the first load step of any law), solved over z-slabs.
 
     world=(dist, rank, size): one slab per process, NCCL collectives.  world=None: `nslabs` slabs in this process on
     one GPU (test mode)."""
@@ -381,3 +388,136 @@ class SlabRVE:
         for s in self.slabs:
             s.close()
         self.slabs = []
+
+
+# ------------------------------------------------------------------------------------------------ product path (C++ host)
+class SlabHandle(C.Structure):
+    """micropp3x_slab_handle (include/micropp_b200_ext.h)."""
+    _fields_ = [("mail", C.c_char * 64), ("p", C.c_char * 64), ("nzl", C.c_longlong), ("nn_pad", C.c_longlong),
+                ("op", C.c_int), ("pad", C.c_int)]
+
+
+def _bind_cxx(lib):
+    if getattr(lib, "_slab_cxx_bound", False):
+        return
+    V = C.c_void_p
+    PP = C.POINTER(Micropp3Params)
+    sig = {
+        "micropp3x_slab_new": (V, [PP, C.c_int, C.c_int, C.c_int]), "micropp3x_slab_free": (None, [V]),
+        "micropp3x_slab_export": (None, [V, C.POINTER(SlabHandle)]),
+        "micropp3x_slab_connect": (None, [V, C.POINTER(SlabHandle)]),
+        "micropp3x_slab_connect_local": (None, [C.POINTER(V), C.c_int]),
+        "micropp3x_slab_homogenize": (C.c_int, [V, _dp, _dp, _ip]),
+        "micropp3x_slab_homogenize_local": (C.c_int, [C.POINTER(V), C.c_int, _dp, _dp, _ip]),
+        "micropp3x_slab_planes": (None, [V, _ip, _ip]), "micropp3x_slab_get_u": (None, [V, _dp]),
+        "micropp3x_slab_launch_count": (C.c_ulonglong, [V]), "micropp3x_slab_operator": (C.c_int, [V]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    lib._slab_cxx_bound = True
+
+
+def _cparams(p):
+    cp = Micropp3Params()
+    cp.ngp = 1
+    cp.size[:] = [int(v) for v in p["size"]]
+    cp.type = int(p["type"])
+    cp.geo_params[:] = [float(v) for v in p["geo_params"]]
+    for i, m in enumerate(p["materials"][:3]):
+        cp.mat_type[i] = int(m[0])
+        cp.mat_E[i], cp.mat_nu[i], cp.mat_Ka[i], cp.mat_Sy[i], cp.mat_Xt[i] = [float(v) for v in m[1:6]]
+    cp.nr_max_its, cp.nr_max_tol, cp.nr_rel_tol = int(p["nr_max_its"]), float(p["nr_max_tol"]), float(p["nr_rel_tol"])
+    return cp
+
+
+class SlabRVECxx:
+    """One RVE over z-slabs, driven by the C++ host (micropp3x_slab_*): peer-memory exchange, fused reductions, CUDA-graph
+    chunks of DPCG iterations.  world=(dist, rank, size): one slab per process; world=None: `nslabs` slabs in-process."""
+
+    exchange = "peer"
+
+    def __init__(self, params: dict, *, world=None, nslabs: int = 1, device: int = 0):
+        self.lib = load()
+        _bind_cxx(self.lib)
+        p = default_params(**params)
+        self.dims = tuple(int(v) for v in p["size"])
+        cp = _cparams(p)
+        self.world = world
+        V = C.c_void_p
+        if world is not None:
+            self.dist, self.rank, self.size = world
+            h = self.lib.micropp3x_slab_new(C.byref(cp), self.rank, self.size, device)
+            if not h:
+                raise ValueError("more slabs than node planes")
+            self.slabs = [V(h)]
+            mine = SlabHandle()
+            self.lib.micropp3x_slab_export(self.slabs[0], C.byref(mine))
+            allraw = [None] * self.size
+            self.dist.all_gather_object(allraw, bytes(mine))          # the only collective: set-up
+            arr = (SlabHandle * self.size)(*[SlabHandle.from_buffer_copy(b) for b in allraw])
+            self.lib.micropp3x_slab_connect(self.slabs[0], arr)
+            self.dist.barrier()
+        else:
+            self.dist, self.rank, self.size = None, 0, nslabs
+            hs = [self.lib.micropp3x_slab_new(C.byref(cp), r, nslabs, device) for r in range(nslabs)]
+            if not all(hs):
+                raise ValueError("more slabs than node planes")
+            self.slabs = [V(h) for h in hs]
+            self._group = (V * nslabs)(*self.slabs)
+            self.lib.micropp3x_slab_connect_local(self._group, nslabs)
+        self.op = int(self.lib.micropp3x_slab_operator(self.slabs[0]))
+        self.exchanges = 0      # halo pulls / cross-rank sums (derived from the iteration counts: the loop is device-side)
+        self.allreduces = 0
+        self._err = 0
+
+    def homogenize(self, eps) -> dict:
+        e = np.ascontiguousarray(eps, dtype=np.float64)
+        sig = np.zeros(6)
+        out = (C.c_int * 3)()
+        if self.world is not None:
+            rc = self.lib.micropp3x_slab_homogenize(self.slabs[0], e.ctypes.data_as(_dp), sig.ctypes.data_as(_dp), out)
+        else:
+            rc = self.lib.micropp3x_slab_homogenize_local(self._group, len(self.slabs), e.ctypes.data_as(_dp),
+                                                          sig.ctypes.data_as(_dp), out)
+        if rc in (-1, -2):
+            raise RuntimeError("micropp3x_slab_homogenize refused the call (see stderr): rc = %d" % rc)
+        self._err = 1 if rc == -3 else 0
+        self.exchanges += int(out[1])
+        self.allreduces += 2 * int(out[1]) + int(out[0]) + 2
+        return dict(stress=sig, newton_its=int(out[0]), cg_its=int(out[1]), converged=bool(out[2]))
+
+    def get_u(self) -> np.ndarray:
+        """Displacements of the owned planes of this process's slabs, reference layout [node][3], global z order."""
+        nx, ny, nz = self.dims
+        parts = []
+        for s in self.slabs:
+            z0, z1 = C.c_int(), C.c_int()
+            self.lib.micropp3x_slab_planes(s, C.byref(z0), C.byref(z1))
+            lo, hi = int(z0.value > 0), int(z1.value < nz)
+            nzl = z1.value + hi - (z0.value - lo)
+            buf = np.zeros(3 * nx * ny * nzl)
+            self.lib.micropp3x_slab_get_u(s, buf.ctypes.data_as(_dp))
+            parts.append(buf.reshape(nzl, ny * nx, 3)[lo:lo + z1.value - z0.value])
+        return np.concatenate(parts, axis=0).reshape(-1, 3)
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.micropp3x_slab_launch_count(s)) for s in self.slabs)
+
+    def peer_error(self) -> int:
+        return self._err
+
+    def close(self):
+        if self.world is not None and self.slabs:
+            self.dist.barrier()          # nobody unmaps memory a neighbour may still read
+        for s in self.slabs:
+            self.lib.micropp3x_slab_free(s)
+        self.slabs = []
+
+
+def SlabRVE(params: dict, *, world=None, nslabs: int = 1, device: int = 0, cg_chunk: int = 8, exchange: str = "peer"):
+    """One RVE solved over z-slabs.  exchange="peer" (default): the product path, host logic in C++ (SlabRVECxx);
+    exchange="nccl": the Python-driven baseline transport (SlabRVEPy)."""
+    if exchange == "peer":
+        return SlabRVECxx(params, world=world, nslabs=nslabs, device=device)
+    return SlabRVEPy(params, world=world, nslabs=nslabs, device=device, cg_chunk=cg_chunk, exchange=exchange)

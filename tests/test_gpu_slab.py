@@ -67,3 +67,29 @@ def test_plane_ranges():
         for r in (1, 2, 3, 4, 8):
             rr = [plane_range(nz, r, s) for s in range(r)]
             assert rr[0][0] == 0 and rr[-1][1] == nz and all(a[1] == b[0] for a, b in zip(rr[:-1], rr[1:]))
+
+
+def test_slab_host_is_cxx_and_refuses_history(mpp):
+    """The product path of the slab mode is the C++ host behind micropp3x_slab_* (include/micropp_b200_ext.h); it keeps
+    no internal variables between calls, so a damage RVE may be solved once (virgin state) and a second call is refused
+    loudly instead of silently using 'no history'."""
+    from micropp_b200.slab import SlabRVE, SlabRVECxx
+    kw = dict(size=(8, 8, 9), lin_stress=False, calc_ctan_lin=False, nr_max_its=10, **CASES["damage_sphere"])
+    rve = SlabRVE(kw, nslabs=2)
+    assert isinstance(rve, SlabRVECxx) and rve.op == 0        # a damage phase: every slab on its own ELL matrix
+    out = rve.homogenize(np.array([0.012, 0, 0, 0, 0, 0.0]))
+    one = mpp.Micropp3(mpp.default_params(**kw))
+    one.set_strain(0, np.array([0.012, 0, 0, 0, 0, 0.0]))
+    one.homogenize()
+    assert out["converged"] == one.has_converged(0) and relerr(out["stress"], one.get_stress(0)) < 1e-8
+    assert rve.launch_count() > 0
+    with pytest.raises(RuntimeError):
+        rve.homogenize(np.array([0.013, 0, 0, 0, 0, 0.0]))
+    rve.close()
+    kw = dict(size=(8, 8, 9), lin_stress=False, calc_ctan_lin=False, **CASES["elastic_sphere"])
+    rve = SlabRVE(kw, nslabs=3)
+    assert rve.op == 3                                        # all-elastic: the implicit operator on every slab
+    a = rve.homogenize(np.array([1e-3, 0, 0, 0, 0, 0.0]))
+    b = rve.homogenize(np.array([1e-3, 0, 0, 0, 0, 0.0]))    # elastic: repeatable, bit for bit
+    assert np.array_equal(a["stress"], b["stress"]) and a["cg_its"] == b["cg_its"]
+    rve.close()
