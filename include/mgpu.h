@@ -147,19 +147,19 @@ int mgpu_newton_step_graph(mgpu_ctx *, int n_active, int use_shared);
    reducing kernel and its scalar tail, and exchanges the halo planes of p before every SpMV ---- */
 void mgpu_tail(mgpu_ctx *, int which_list, int n, int kind /*0 rhs,1 cg_init,2 spmv,3 cg_update,4 ave_stress*/, int mode);
 /* ---- slab mode over peer memory (NVLink P2P; no collective library in the DPCG loop) ----
-   Every rank owns a mailbox that all ranks map (mgpu_ipc_export / mgpu_ipc_open); slab-local sums are posted there with
-   an epoch and summed in rank order by every rank's tail kernel; halo planes of p are pulled from the neighbours'
-   vectors once their owner has published the epoch of its last p update.  All device-side waits are bounded. */
+   Every rank owns a mailbox that all ranks map (mgpu_ipc_export / mgpu_ipc_open); slab-local sums are PUSHED into every
+   rank's mailbox with an epoch and summed in rank order by every rank's reduce_tail kernel (waiting on local memory
+   only); the p update pushes its boundary planes into the neighbours' receive buffers and releases an epoch flag in
+   their mailboxes.  No remote load anywhere on the critical path.  All device-side waits are bounded. */
 void *mgpu_slab_mail(mgpu_ctx *);
 void mgpu_ipc_export(void *devptr, char *handle64);
 void *mgpu_ipc_open(int device, const char *handle64);
 void mgpu_ipc_close(void *mapped);
-void mgpu_slab_link(mgpu_ctx *, int rank, int size, void *const *mails, const void *p_lo, long long lo_off,
-                    long long lo_npad, const void *p_hi, long long hi_off, long long hi_npad);
-void mgpu_slab_publish_p(mgpu_ctx *);
-void mgpu_slab_halo_pull(mgpu_ctx *);
-void mgpu_slab_post(mgpu_ctx *, int k);
-void mgpu_slab_gather_tail(mgpu_ctx *, int which_list, int k, int kind, int mode); /* kind / mode as mgpu_tail */
+/* mails[r]: mailbox of rank r as mapped here (r == rank: the own one).  A mailbox allocation also holds the two receive
+   buffers of the halo planes, so one IPC handle per rank is all that travels */
+void mgpu_slab_link(mgpu_ctx *, int rank, int size, void *const *mails);
+void mgpu_slab_push_p(mgpu_ctx *);     /* p as it stands -> the neighbours' receive buffers + epoch flags (once per solve) */
+void mgpu_slab_halo_take(mgpu_ctx *);  /* wait on own memory for the neighbours' pushes, copy them into the halo planes */
 /* fused path (one launch per cross-rank reduction: fold + post + gather + tail; the p update publishes its epoch) */
 void mgpu_slab_set_fused(mgpu_ctx *, int on);
 void mgpu_slab_reduce_tail(mgpu_ctx *, int which_list, int k, int kind, int mode);

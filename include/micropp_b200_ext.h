@@ -93,10 +93,7 @@ struct mgpu_ctx *micropp3x_slab_create(const struct micropp3_params *params, int
    out3 = {Newton iterations, DPCG iterations, converged}.  Returns 0, or < 0 on misuse / a lost peer. */
 struct micropp3x_slab;
 struct micropp3x_slab_handle {
-  char mail[64];      /* CUDA IPC handle of this rank's mailbox */
-  char p[64];         /* CUDA IPC handle of this rank's search-direction vector */
-  long long nzl;      /* local node planes (halo planes included) */
-  long long nn_pad;   /* component stride of the local vectors */
+  char mail[64];      /* CUDA IPC handle of this rank's mailbox + halo receive buffers (one allocation) */
   int op, pad;        /* DPCG operator this rank would choose alone (3 implicit, 0 assembled) */
 };
 struct micropp3x_slab *micropp3x_slab_new(const struct micropp3_params *params, int rank, int size, int device);

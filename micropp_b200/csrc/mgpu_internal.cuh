@@ -336,18 +336,34 @@ struct TileInfo2 {
 };
 
 // ---- slab mode over peer memory ---------------------------------------------------------------------------
+constexpr int SLAB_MAX_RANKS = 16;
+// Mailbox of one rank, mapped by every rank (CUDA IPC).  Cross-rank sums are PUSHED: rank s writes its slab-local sums
+// into in[parity][s][*] of EVERY rank's mailbox (remote stores over NVLink, one lane per destination), then releases
+// in_epoch[s]; a rank waits on its OWN memory only and adds the contributions in rank order.  Two buffers (epoch parity)
+// suffice: a rank can post epoch e + 2 only after reduction e + 1 completed, which needs every rank's post of e + 1,
+// i.e. every rank has finished reading epoch e.
 struct SlabMail {
-  double red[2][8];
-  unsigned long long red_epoch, p_epoch;  // published epochs (read by the peers)
+  double in[2][SLAB_MAX_RANKS][8];
+  unsigned long long in_epoch[SLAB_MAX_RANKS];  // epoch of the last post of rank s (written by s)
+  unsigned long long p_in_epoch[2];             // epoch of the halo plane PUSHED by the lower [0] / upper [1] neighbour
   unsigned long long red_local, p_local;  // the owner's own counters: the epochs live on the device, so a whole chunk
                                           // of DPCG iterations is a replayable CUDA graph with constant arguments
   int error;
   unsigned pub_ticket;  // blocks of the p update that have finished (the last one publishes the epoch)
 };
-constexpr int SLAB_MAX_RANKS = 16;
+
 struct SlabPeers {
   SlabMail *mail[SLAB_MAX_RANKS];
 };
+// where this rank's boundary planes of p go: the neighbours' RECEIVE buffers (peer-mapped; they follow the SlabMail in
+// the same allocation: [side][component][nx*ny], side 0 = from the lower neighbour, 1 = from the upper one) and the
+// neighbours' mailboxes for the epoch flags.  The receiver copies a buffer into its halo plane of p in its own stream
+// order (k_slab_halo_take) -- pushing into p itself would race with the receiver's own use of the halo values.
+struct SlabHalo {
+  double *in_lo, *in_hi;  // the lower neighbour's side-1 buffer / the upper neighbour's side-0 buffer (null at the ends)
+  SlabMail *mail_lo, *mail_hi;
+};
+__host__ __device__ inline size_t slab_mail_bytes() { return (sizeof(SlabMail) + 255) / 256 * 256; }
 
 }  // namespace mgpu_int
 
@@ -377,8 +393,7 @@ struct mgpu_ctx {
   bool slab_fused = false;
   int last_spmv_nfold = 0, last_update_nblk = 0;
   int slab_launches_per_chunk = 0;
-  const double *slab_p_lo = nullptr, *slab_p_hi = nullptr;
-  long long slab_lo_off = 0, slab_lo_npad = 0, slab_hi_off = 0, slab_hi_npad = 0;
+  mgpu_int::SlabHalo slab_halo{};
   mgpu_int::TileInfo2 tile2;        // tiling of k_spmv_dot_tmac (7 or 8 nodes per thread, two lane shapes)
   CUtensorMap tmap_a, tmap_b;  // V.p with the boxes of lane shape 0 (pitch x 10 x 6) and 1 (pitch x 6 x 10)
   CUtensorMap smap_a, smap_b;  // V.Ap with the store boxes (cb*tn x 8 x 4) and (cb*tn x 4 x 8)

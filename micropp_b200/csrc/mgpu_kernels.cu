@@ -666,12 +666,22 @@ __global__ void __launch_bounds__(NT, 4)
   }
 }
 
-// `publish` (slab mode over peer memory, fused path): the LAST of the blocks that write a halo-relevant plane -- ticket in
-// the mailbox -- publishes the epoch of this p update, so the neighbours' halo pull needs no extra launch.  The
-// tickets are taken also when the slot has already left the loop (all ranks run the same launch sequence).
-__device__ __forceinline__ void slab_publish_after_update(const MeshConst &P, SlabMail *mail) {
-  // only the blocks that write the two planes a neighbour pulls (the bottom and top OWNED planes: local planes 1 and
-  // nz - 2) take part: a system-scope fence + ticket in all 62 500 blocks of a 200^3 slab costs more than the update
+// Slab mode over peer memory: the p update PUSHES the new values of its two boundary planes (the bottom and top OWNED
+// planes: local planes 1 and nz - 2) into the neighbours' receive buffers -- remote stores over NVLink, fire and
+// forget -- and the LAST of the blocks that write such a plane (ticket in the own mailbox) releases the epoch flag in
+// the NEIGHBOURS' mailboxes.  The receiver only waits on its own memory and copies the buffer into its halo plane
+// (k_slab_halo_take): no remote load, no round trip on the critical path.  Tickets are taken also when the slot has already left the loop (all ranks run
+// the same launch sequence).
+__device__ __forceinline__ bool slab_halo_node(const MeshConst &P, int n) {
+  const int k = n / P.nxny;
+  return (k == 0 && P.halo_lo) || (k == P.nz - 1 && P.halo_hi);
+}
+__device__ __forceinline__ void slab_push_value(const MeshConst &P, const SlabHalo &H, int n, int d, double v) {
+  const int k = n / P.nxny, r = n - k * P.nxny;
+  if (k == 1 && H.in_lo) H.in_lo[(size_t)d * P.nxny + r] = v;
+  if (k == P.nz - 2 && H.in_hi) H.in_hi[(size_t)d * P.nxny + r] = v;
+}
+__device__ __forceinline__ void slab_publish_after_update(const MeshConst &P, const SlabHalo &H, SlabMail *mail) {
   const int lo1 = P.nxny / NT, hi1 = (2 * P.nxny - 1) / NT;
   const int lo2 = ((P.nz - 2) * P.nxny) / NT, hi2 = ((P.nz - 1) * P.nxny - 1) / NT;
   const int b = blockIdx.x;
@@ -686,13 +696,16 @@ __device__ __forceinline__ void slab_publish_after_update(const MeshConst &P, Sl
       mail->pub_ticket = 0u;
       const unsigned long long epoch = ++mail->p_local;
       __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&mail->p_epoch), "l"(epoch) : "memory");
+      // I am the UPPER neighbour of mail_lo's owner and the LOWER neighbour of mail_hi's owner
+      if (H.mail_lo) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&H.mail_lo->p_in_epoch[1]), "l"(epoch) : "memory");
+      if (H.mail_hi) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&H.mail_hi->p_in_epoch[0]), "l"(epoch) : "memory");
     }
   }
 }
 
 __global__ void __launch_bounds__(NT)
-    k_cg_pupdate_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, SlabMail *publish) {
+    k_cg_pupdate_imp(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, SlabMail *publish,
+                     const SlabHalo H) {
   const int slot = slot_of(L);
   const int n = blockIdx.x * NT + threadIdx.x;
   if (slot >= 0 && T.state[slot].cg_active && n < P.nn) {
@@ -705,10 +718,12 @@ __global__ void __launch_bounds__(NT)
       const double z = __dmul_rn(imp_kk(P, V, n, d), V.r[ix]);  // never fused into the FMA below
       const double pp = V.p[ix];
       V.du[ix] = fma(alpha, pp, V.du[ix]);  // x += alpha p of this iteration (src/ell.cpp:102)
-      V.p[ix] = z + beta * pp;
+      const double pn = z + beta * pp;
+      if (!publish || !slab_halo_node(P, n)) V.p[ix] = pn;  // halo entries of p are the neighbour's values
+      if (publish) slab_push_value(P, H, n, d, pn);
     }
   }
-  if (publish) slab_publish_after_update(P, publish);
+  if (publish) slab_publish_after_update(P, H, publish);
 }
 
 // Arbitrary user matrix in the reference's own layout vals[row*81 + slot] (host-pointer ell_mvp / ell_solve_cgpd
@@ -808,7 +823,8 @@ __global__ void __launch_bounds__(NT, 4)
 
 // p = z + beta p (src/ell.cpp:113); skipped once the slot has left the loop (p is dead then).
 __global__ void __launch_bounds__(NT)
-    k_cg_pupdate(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, SlabMail *publish) {
+    k_cg_pupdate(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, SlabMail *publish,
+                 const SlabHalo H) {
   const int slot = slot_of(L);
   const int n = blockIdx.x * NT + threadIdx.x;
   if (slot >= 0 && T.state[slot].cg_active && n < P.nn) {
@@ -820,10 +836,12 @@ __global__ void __launch_bounds__(NT)
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
       const double pp = V.p[ix];
       V.du[ix] = fma(alpha, pp, V.du[ix]);  // x += alpha p of this iteration (src/ell.cpp:102)
-      V.p[ix] = V.z[ix] + beta * pp;
+      const double pn = V.z[ix] + beta * pp;
+      if (!publish || !slab_halo_node(P, n)) V.p[ix] = pn;  // halo entries of p are the neighbour's values
+      if (publish) slab_push_value(P, H, n, d, pn);
     }
   }
-  if (publish) slab_publish_after_update(P, publish);
+  if (publish) slab_publish_after_update(P, H, publish);
 }
 
 // x += alpha p of the LAST iteration of every slot of the list that iterated at all: its p update was skipped because
@@ -1019,8 +1037,9 @@ __global__ void k_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTab
 //    are posted there with an epoch number (st.release.sys); the tail kernel of every rank waits for the epoch of
 //    every mailbox (ld.acquire.sys), adds the partial sums in RANK ORDER (identical bits on all ranks) and runs the
 //    reference's scalar logic -- an all-reduce of <= 6 doubles costs two tiny kernels instead of a collective;
-//  * the halo planes of p are PULLED from the neighbours' vectors by k_slab_halo_pull once the neighbour has
-//    published the epoch of its last p update.
+//  * the halo planes of p are PUSHED into the neighbours' receive buffers by the p update itself (k_cg_pupdate*),
+//    followed by an epoch flag in the neighbours' mailboxes; the receiver waits on its own memory and copies the
+//    buffer into its halo plane (k_slab_halo_take).
 // Write-after-read safety needs no extra flag: a rank overwrites p (next p update) only after the tail of the
 // following reduction, which cannot complete before every neighbour has posted its partial sum, i.e. has finished
 // the SpMV that followed its pull.  Two mailbox buffers (epoch parity) are enough for the same reason.
@@ -1044,81 +1063,60 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
   return true;
 }
 
-__global__ void k_slab_publish_p(SlabMail *mail) {
-  const unsigned long long epoch = ++mail->p_local;
+// p as it stands (after cg_init: p = z) -> the neighbours' receive buffers + their epoch flags; one launch per solve
+__global__ void __launch_bounds__(NT)
+    k_slab_push_p(const __grid_constant__ MeshConst P, const double *p_own, SlabMail *own, const SlabHalo H) {
+  // blockIdx.y = 0: bottom owned plane -> lower neighbour, 1: top owned plane -> upper neighbour
+  const bool hi = blockIdx.y == 1;
+  double *dst = hi ? H.in_hi : H.in_lo;
+  if (dst) {
+    const double *src = p_own + (size_t)(hi ? P.nz - 2 : 1) * P.nxny;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < P.nxny; i += gridDim.x * NT) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dst[(size_t)d * P.nxny + i] = src[(size_t)d * P.nn_pad + i];
+    }
+  }
   __threadfence_system();
-  st_release_sys(&mail->p_epoch, epoch);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&own->pub_ticket, 1u);
+    if (t == gridDim.x * gridDim.y - 1) {
+      own->pub_ticket = 0u;
+      const unsigned long long epoch = ++own->p_local;
+      __threadfence_system();
+      if (H.mail_lo) st_release_sys(&H.mail_lo->p_in_epoch[1], epoch);
+      if (H.mail_hi) st_release_sys(&H.mail_hi->p_in_epoch[0], epoch);
+    }
+  }
 }
 
-// blockIdx.y = 0: low halo plane <- neighbour below, 1: high halo plane <- neighbour above
-__global__ void __launch_bounds__(NT)
-    k_slab_halo_pull(const __grid_constant__ MeshConst P, double *p_own, SlabMail *own, const double *p_lo,
-                     long long lo_off, long long lo_npad, const SlabMail *mail_lo, const double *p_hi, long long hi_off,
-                     long long hi_npad, const SlabMail *mail_hi) {
+// wait (on OWN memory) until the neighbour has pushed the plane that belongs to the p update this rank has done itself,
+// then copy it from the receive buffer into the halo plane of p.  blockIdx.y = 0: lower halo plane, 1: upper one
+__global__ void __launch_bounds__(NT) k_slab_halo_take(const __grid_constant__ MeshConst P, double *p_own, SlabMail *own) {
   const bool hi = blockIdx.y == 1;
-  const double *src = hi ? p_hi : p_lo;
-  if (!src) return;
+  if (hi ? !P.halo_hi : !P.halo_lo) return;
   __shared__ int ok;
   if (threadIdx.x == 0) {
-    const unsigned long long epoch = own->p_local;  // as many publishes as this rank has done itself
-    ok = spin_until(hi ? &mail_hi->p_epoch : &mail_lo->p_epoch, epoch);
+    ok = spin_until(&own->p_in_epoch[hi ? 1 : 0], own->p_local);
     if (!ok) own->error = 1;
   }
   __syncthreads();
   if (!ok) return;
-  const long long off = hi ? hi_off : lo_off, npad = hi ? hi_npad : lo_npad;
+  const double *src = reinterpret_cast<const double *>(reinterpret_cast<const char *>(own) + slab_mail_bytes()) +
+                      (size_t)(hi ? 1 : 0) * 3 * P.nxny;
   double *dst = p_own + (size_t)(hi ? P.nz - 1 : 0) * P.nxny;
   for (int i = blockIdx.x * NT + threadIdx.x; i < P.nxny; i += gridDim.x * NT) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) dst[(size_t)d * P.nn_pad + i] = __ldcv(src + (size_t)d * npad + off + i);
-  }
-}
-
-__global__ void k_slab_post(const double *red, SlabMail *mail, int k) {
-  if (threadIdx.x != 0) return;
-  const unsigned long long epoch = ++mail->red_local;
-  for (int q = 0; q < k; ++q) mail->red[epoch & 1][q] = red[q];
-  __threadfence_system();
-  st_release_sys(&mail->red_epoch, epoch);
-}
-
-// sum of the posted slab sums in rank order, then the scalar tail (k_tail) on this rank
-__global__ void k_slab_gather_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
-                                   const __grid_constant__ SlabPeers peers, SlabMail *own, int nranks, int k,
-                                   int kind, int mode) {
-  const int slot = slot_of(L);
-  if (slot < 0 || threadIdx.x != 0) return;
-  const unsigned long long epoch = own->red_local;
-  double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int r = 0; r < nranks; ++r) {
-    if (!spin_until(&peers.mail[r]->red_epoch, epoch)) own->error = 1;
-    for (int q = 0; q < k; ++q) tot[q] += __ldcv(&peers.mail[r]->red[epoch & 1][q]);
-  }
-  double *red = T.red + slot * 8;
-  for (int q = 0; q < k; ++q) red[q] = tot[q];
-  mgpu_slot_state *st = &T.state[slot];
-  switch (kind) {
-    case 0:
-      if (mode == 1 && !st->nr_active) return;
-      tail_rhs(P, st, red[0], mode);
-      break;
-    case 1: tail_cg_init(P, st, red[0], red[1]); break;
-    case 2:
-      if (st->cg_active) tail_spmv(st, red[0]);
-      break;
-    case 3:
-      if (st->cg_active) tail_cg_update(P, st, red[0], red[1]);
-      break;
-    default:
-      for (int q = 0; q < 6; ++q) T.stress[slot * 6 + q] = red[q] / 1.0;
-      break;
+    for (int d = 0; d < 3; ++d) dst[(size_t)d * P.nn_pad + i] = __ldcv(src + (size_t)d * P.nxny + i);
   }
 }
 
 // Fused cross-rank reduction of the slab mode: ONE warp folds the slab-local partial sums of the preceding kernel
 // (kind 2: p.Ap partials of the SpMV; kind 3: z.z / r.z partials of the r update; other kinds: T.red as their ticket
-// reductions left it), posts them in the mailbox, waits for every rank's post, adds them in RANK ORDER and runs the
-// scalar tail -- what used to be k_fold_* + k_slab_post + k_slab_gather_tail, three launches per reduction.
+// reductions left it), PUSHES them into every rank's mailbox (one lane per destination: the NVLink stores go out in
+// parallel), waits on its own memory for every rank's contribution, adds them in RANK ORDER and runs the scalar tail.
+// One launch per reduction, and no remote load on the critical path (a remote poll costs a NVLink round trip per
+// rank: 8 ranks x 2 loads in sequence were ~25 us per reduction).
 // sum of n partials by the whole block in a fixed order (strided per-thread sums, then a fixed tree): deterministic;
 // result valid in thread 0.  A 200^3 slab leaves tens of thousands of partials -- too many for one warp.
 __device__ __forceinline__ double block_fold(const double *partial, int n, double *sm /* [blockDim.x / 32] */) {
@@ -1135,8 +1133,8 @@ __device__ __forceinline__ double block_fold(const double *partial, int n, doubl
 }
 
 __global__ void k_slab_reduce_tail(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
-                                   const __grid_constant__ SlabPeers peers, SlabMail *own, int nranks, int k, int kind,
-                                   int mode, int nfold) {
+                                   const __grid_constant__ SlabPeers peers, SlabMail *own, int myrank, int nranks,
+                                   int k, int kind, int mode, int nfold) {
   __shared__ double sm[32];
   const int slot = slot_of(L);
   if (slot < 0) return;
@@ -1152,16 +1150,26 @@ __global__ void k_slab_reduce_tail(const __grid_constant__ MeshConst P, const Ls
       red[1] = rz;
     }
   }
-  if (threadIdx.x != 0) return;
-  const unsigned long long epoch = ++own->red_local;
-  for (int q = 0; q < k; ++q) own->red[epoch & 1][q] = red[q];
-  __threadfence_system();
-  st_release_sys(&own->red_epoch, epoch);
-  double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int r = 0; r < nranks; ++r) {
-    if (!spin_until(&peers.mail[r]->red_epoch, epoch)) own->error = 1;
-    for (int q = 0; q < k; ++q) tot[q] += __ldcv(&peers.mail[r]->red[epoch & 1][q]);
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  // push: lane r writes this rank's sums into rank r's mailbox, then releases its flag there
+  const int lane = threadIdx.x;
+  unsigned long long epoch = 0;
+  if (lane == 0) epoch = ++own->red_local;
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  if (lane < nranks) {
+    SlabMail *dst = peers.mail[lane];
+    for (int q = 0; q < k; ++q) dst->in[epoch & 1][myrank][q] = red[q];
+    __threadfence_system();
+    st_release_sys(&dst->in_epoch[myrank], epoch);
+    // wait (on LOCAL memory) for rank `lane`'s contribution
+    if (!spin_until(&own->in_epoch[lane], epoch)) own->error = 1;
   }
+  __syncwarp();
+  if (lane != 0) return;
+  double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < nranks; ++r)  // rank order: identical bits on every rank
+    for (int q = 0; q < k; ++q) tot[q] += __ldcv(&own->in[epoch & 1][r][q]);
   for (int q = 0; q < k; ++q) red[q] = tot[q];
   mgpu_slot_state *st = &T.state[slot];
   switch (kind) {
@@ -1871,10 +1879,10 @@ void mgpu_cg_pupdate(mgpu_ctx *c, int l, int n) {
   ProfScope ps(c, 3, n);
   if (c->cg_op == OP_IMPLICIT)
     k_cg_pupdate_imp<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V,
-                                                            c->slab_fused ? c->slab_mail : nullptr);
+                                                            c->slab_fused ? c->slab_mail : nullptr, c->slab_halo);
   else
     k_cg_pupdate<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V,
-                                                        c->slab_fused ? c->slab_mail : nullptr);
+                                                        c->slab_fused ? c->slab_mail : nullptr, c->slab_halo);
   CK(cudaGetLastError());
 }
 void mgpu_cg_finish(mgpu_ctx *c, int l, int n) {
@@ -2069,8 +2077,10 @@ extern "C" {
 void *mgpu_slab_mail(mgpu_ctx *c) {
   CK(cudaSetDevice(c->device));
   if (!c->slab_mail) {
-    CK(cudaMalloc(&c->slab_mail, sizeof(SlabMail)));
-    CK(cudaMemset(c->slab_mail, 0, sizeof(SlabMail)));
+    // the mailbox and, in the same allocation (one IPC handle), the two receive buffers of the halo planes
+    const size_t bytes = slab_mail_bytes() + sizeof(double) * 2 * 3 * (size_t)c->mc.nxny;
+    CK(cudaMalloc((void **)&c->slab_mail, bytes));
+    CK(cudaMemset(c->slab_mail, 0, bytes));
     CK(cudaDeviceSynchronize());
   }
   return c->slab_mail;
@@ -2093,8 +2103,7 @@ void mgpu_ipc_close(void *p) { cudaIpcCloseMemHandle(p); }
 // mails[r]: mailbox of rank r as mapped here (r == rank: the own one); p_lo / p_hi: the neighbours' p vectors
 // (null at the ends), *_off: offset (doubles, component 0) of the neighbour's owned plane next to the cut,
 // *_npad: the neighbour's component stride
-void mgpu_slab_link(mgpu_ctx *c, int rank, int size, void *const *mails, const void *p_lo, long long lo_off,
-                    long long lo_npad, const void *p_hi, long long hi_off, long long hi_npad) {
+void mgpu_slab_link(mgpu_ctx *c, int rank, int size, void *const *mails) {
   if (size > SLAB_MAX_RANKS) {
     fprintf(stderr, "micropp-b200: at most %d slabs\n", SLAB_MAX_RANKS);
     abort();
@@ -2103,36 +2112,27 @@ void mgpu_slab_link(mgpu_ctx *c, int rank, int size, void *const *mails, const v
   c->slab_rank = rank;
   c->slab_size = size;
   for (int r = 0; r < size; ++r) c->slab_peers.mail[r] = (SlabMail *)mails[r];
-  c->slab_p_lo = (const double *)p_lo;
-  c->slab_p_hi = (const double *)p_hi;
-  c->slab_lo_off = lo_off;
-  c->slab_lo_npad = lo_npad;
-  c->slab_hi_off = hi_off;
-  c->slab_hi_npad = hi_npad;
+  SlabHalo &H = c->slab_halo;
+  H.mail_lo = rank > 0 ? c->slab_peers.mail[rank - 1] : nullptr;
+  H.mail_hi = rank + 1 < size ? c->slab_peers.mail[rank + 1] : nullptr;
+  auto buf = [&](SlabMail *m, int side) {
+    return reinterpret_cast<double *>(reinterpret_cast<char *>(m) + slab_mail_bytes()) + (size_t)side * 3 * c->mc.nxny;
+  };
+  H.in_lo = H.mail_lo ? buf(H.mail_lo, 1) : nullptr;  // I am the lower neighbour's UPPER neighbour
+  H.in_hi = H.mail_hi ? buf(H.mail_hi, 0) : nullptr;
 }
-void mgpu_slab_publish_p(mgpu_ctx *c) {
+// p (as it stands) -> the neighbours' halo planes; once per solve, after cg_init
+void mgpu_slab_push_p(mgpu_ctx *c) {
   c->launches++;
-  k_slab_publish_p<<<1, 1, 0, c->stream>>>(c->slab_mail);
+  const int nb = std::max(1, (c->mc.nxny + NT - 1) / NT);
+  k_slab_push_p<<<dim3(nb, 2), NT, 0, c->stream>>>(c->mc, c->V.p, c->slab_mail, c->slab_halo);
   CK(cudaGetLastError());
 }
-void mgpu_slab_halo_pull(mgpu_ctx *c) {
+void mgpu_slab_halo_take(mgpu_ctx *c) {
+  if (!c->mc.halo_lo && !c->mc.halo_hi) return;
   c->launches++;
-  const int nb = std::min(64, (c->mc.nxny + NT - 1) / NT);
-  k_slab_halo_pull<<<dim3(nb, 2), NT, 0, c->stream>>>(
-      c->mc, c->V.p, c->slab_mail, c->slab_p_lo, c->slab_lo_off, c->slab_lo_npad,
-      c->slab_rank > 0 ? c->slab_peers.mail[c->slab_rank - 1] : nullptr, c->slab_p_hi, c->slab_hi_off, c->slab_hi_npad,
-      c->slab_rank + 1 < c->slab_size ? c->slab_peers.mail[c->slab_rank + 1] : nullptr);
-  CK(cudaGetLastError());
-}
-void mgpu_slab_post(mgpu_ctx *c, int k) {
-  c->launches++;
-  k_slab_post<<<1, 32, 0, c->stream>>>(c->T.red, c->slab_mail, k);
-  CK(cudaGetLastError());
-}
-void mgpu_slab_gather_tail(mgpu_ctx *c, int l, int k, int kind, int mode) {
-  c->launches++;
-  k_slab_gather_tail<<<dim3(1, 1), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
-                                                      c->slab_size, k, kind, mode);
+  const int nb = std::max(1, (c->mc.nxny + NT - 1) / NT);
+  k_slab_halo_take<<<dim3(nb, 2), NT, 0, c->stream>>>(c->mc, c->V.p, c->slab_mail);
   CK(cudaGetLastError());
 }
 // fused path: on / off (slab_host.cpp switches it on for the whole life of a slab context)
@@ -2143,7 +2143,7 @@ void mgpu_slab_reduce_tail(mgpu_ctx *c, int l, int k, int kind, int mode) {
   const int nfold = kind == 2 ? c->last_spmv_nfold : (kind == 3 ? c->last_update_nblk : 0);
   const int threads = nfold > 4096 ? 1024 : (nfold > 256 ? 256 : 32);
   k_slab_reduce_tail<<<dim3(1, 1), threads, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->slab_peers, c->slab_mail,
-                                                           c->slab_size, k, kind, mode, nfold);
+                                                           c->slab_rank, c->slab_size, k, kind, mode, nfold);
   CK(cudaGetLastError());
 }
 int mgpu_slab_error(mgpu_ctx *c) {
@@ -2154,25 +2154,14 @@ int mgpu_slab_error(mgpu_ctx *c) {
   return m.error;
 }
 // One DPCG iteration of this rank's slab (every rank calls it; no host synchronisation):
-//   unfused: halo pull -> SpMV -> post/tail(p.Ap) -> r, z update -> post/tail(z.z, r.z) -> p, x update -> publish p
-//   fused  : halo pull -> SpMV -> reduce_tail(p.Ap) -> r, z update -> reduce_tail(z.z, r.z) -> p, x update (+ publish)
+//   halo take -> SpMV -> reduce_tail(p.Ap) -> r, z update -> reduce_tail(z.z, r.z) -> p, x update (+ push of its boundary planes)
 void mgpu_slab_cg_iteration(mgpu_ctx *c, int l, int op) {
-  mgpu_slab_halo_pull(c);
+  mgpu_slab_halo_take(c);
   mgpu_cg_spmv_dot(c, l, 1, op);
-  if (c->slab_fused) {
-    mgpu_slab_reduce_tail(c, l, 1, 2, 0);
-    mgpu_cg_update(c, l, 1);
-    mgpu_slab_reduce_tail(c, l, 2, 3, 0);
-    mgpu_cg_pupdate(c, l, 1);
-    return;
-  }
-  mgpu_slab_post(c, 1);
-  mgpu_slab_gather_tail(c, l, 1, 2, 0);
+  mgpu_slab_reduce_tail(c, l, 1, 2, 0);
   mgpu_cg_update(c, l, 1);
-  mgpu_slab_post(c, 2);
-  mgpu_slab_gather_tail(c, l, 2, 3, 0);
+  mgpu_slab_reduce_tail(c, l, 2, 3, 0);
   mgpu_cg_pupdate(c, l, 1);
-  mgpu_slab_publish_p(c);
 }
 // `iters` DPCG iterations of this rank's slab as ONE CUDA graph launch (captured once per (op, iters); the epochs of
 // the cross-rank flags live on the device, so every kernel argument is constant).  Slots that converge inside the

@@ -5,13 +5,14 @@
 //
 // A macro code (C++, C, Fortran through the C ABI) drives it without Python:
 //     s = micropp3x_slab_new(&params, rank, size, device);          // this rank's planes + one halo plane per neighbour
-//     micropp3x_slab_export(s, &mine);                              // CUDA IPC handles of the mailbox and of p
+//     micropp3x_slab_export(s, &mine);                              // CUDA IPC handle of the mailbox (+ receive buffers)
 //     MPI_Allgather(&mine, sizeof mine, MPI_BYTE, all, sizeof mine, MPI_BYTE, comm);      // the ONLY collective: set-up
 //     micropp3x_slab_connect(s, all);
 //     micropp3x_slab_homogenize(s, eps, sig, out);                  // every rank calls it; no host-side communication
-// Inside a solve the ranks talk through NVLink peer memory only: halo planes of p are pulled from the neighbours'
-// vectors, the dot products travel through peer-mapped mailboxes with device-side epoch flags (k_slab_halo_pull,
-// k_slab_reduce_tail in mgpu_kernels.cu), and a chunk of DPCG iterations is one replayed CUDA graph.  Several slabs
+// Inside a solve the ranks talk through NVLink peer memory only, and only by REMOTE STORES: the p update pushes its
+// boundary planes into the neighbours' receive buffers, the slab-local dot products are pushed into every rank's mailbox,
+// each followed by a device-side epoch flag; every wait polls local memory (k_cg_pupdate*, k_slab_halo_take,
+// k_slab_reduce_tail in mgpu_kernels.cu).  A chunk of DPCG iterations is one replayed CUDA graph.  Several slabs
 // may also live in ONE process (micropp3x_slab_connect_local): the same kernels with plain device pointers, used by
 // the single-GPU tests.
 #include <algorithm>
@@ -64,15 +65,8 @@ void each(micropp3x_slab *const *g, int n, F f) {
   for (int i = 0; i < n; ++i) f(g[i]);
 }
 
-void link(micropp3x_slab *s, const std::vector<void *> &mails, const std::vector<const void *> &pptr,
-          const std::vector<long long> &nzl, const std::vector<long long> &npad, const std::vector<int> &ops) {
-  const int r = s->rank, size = s->size;
-  const long long nxny = (long long)s->nx * s->ny;
-  const void *lo = r > 0 ? pptr[r - 1] : nullptr, *hi = r + 1 < size ? pptr[r + 1] : nullptr;
-  const long long lo_off = r > 0 ? (nzl[r - 1] - 2) * nxny : 0;  // the lower neighbour's top owned plane
-  const long long hi_off = r + 1 < size ? nxny : 0;              // the upper neighbour's bottom owned plane
-  mgpu_slab_link(s->ctx, r, size, mails.data(), lo, lo_off, r > 0 ? npad[r - 1] : 0, hi, hi_off,
-                 r + 1 < size ? npad[r + 1] : 0);
+void link(micropp3x_slab *s, const std::vector<void *> &mails, const std::vector<int> &ops) {
+  mgpu_slab_link(s->ctx, s->rank, s->size, mails.data());
   // one operator for the whole RVE: the implicit one only if EVERY slab is all-elastic (a rank deciding from its own
   // elements alone could pick another operator -- and another launch sequence -- than its neighbours)
   s->op = *std::min_element(ops.begin(), ops.end()) >= 3 ? 3 : 0;
@@ -88,7 +82,7 @@ void reduce_tail(micropp3x_slab *const *g, int n, int k, int kind, int mode) {
 void cg_solve(micropp3x_slab *const *g, int n) {
   each(g, n, [&](micropp3x_slab *s) { mgpu_cg_init(s->ctx, kList, 1, s->op); });
   reduce_tail(g, n, 2, 1, 0);
-  each(g, n, [&](micropp3x_slab *s) { mgpu_slab_publish_p(s->ctx); });
+  each(g, n, [&](micropp3x_slab *s) { mgpu_slab_push_p(s->ctx); });
   // every rank takes the same decisions (rank-ordered sums => identical bits), so slab 0 speaks for all
   while (state_of(g[0]).cg_active)
     each(g, n, [&](micropp3x_slab *s) { mgpu_slab_cg_chunk(s->ctx, kList, s->op, s->cg_chunk); });
@@ -182,50 +176,32 @@ void micropp3x_slab_free(micropp3x_slab *s) {
 void micropp3x_slab_export(micropp3x_slab *s, micropp3x_slab_handle *out) {
   memset(out, 0, sizeof(*out));
   mgpu_ipc_export(mgpu_slab_mail(s->ctx), out->mail);
-  mgpu_ipc_export(mgpu_dev_ptr(s->ctx, 3), out->p);
-  out->nzl = s->nzl;
-  out->nn_pad = mgpu_nn_pad(s->ctx);
   out->op = s->op;
 }
 
 void micropp3x_slab_connect(micropp3x_slab *s, const micropp3x_slab_handle *all) {
   std::vector<void *> mails(s->size);
-  std::vector<const void *> pptr(s->size, nullptr);
-  std::vector<long long> nzl(s->size), npad(s->size);
   std::vector<int> ops(s->size);
   for (int r = 0; r < s->size; ++r) {
-    nzl[r] = all[r].nzl;
-    npad[r] = all[r].nn_pad;
     ops[r] = all[r].op;
     if (r == s->rank) {
       mails[r] = mgpu_slab_mail(s->ctx);
-      pptr[r] = mgpu_dev_ptr(s->ctx, 3);
       continue;
     }
     mails[r] = mgpu_ipc_open(s->device, all[r].mail);
     s->mapped.push_back(mails[r]);
-    if (r == s->rank - 1 || r == s->rank + 1) {
-      void *p = mgpu_ipc_open(s->device, all[r].p);
-      s->mapped.push_back(p);
-      pptr[r] = p;
-    }
   }
-  link(s, mails, pptr, nzl, npad, ops);
+  link(s, mails, ops);
 }
 
 void micropp3x_slab_connect_local(micropp3x_slab *const *group, int n) {
   std::vector<void *> mails(n);
-  std::vector<const void *> pptr(n);
-  std::vector<long long> nzl(n), npad(n);
   std::vector<int> ops(n);
   for (int r = 0; r < n; ++r) {
     mails[r] = mgpu_slab_mail(group[r]->ctx);
-    pptr[r] = mgpu_dev_ptr(group[r]->ctx, 3);
-    nzl[r] = group[r]->nzl;
-    npad[r] = mgpu_nn_pad(group[r]->ctx);
     ops[r] = group[r]->op;
   }
-  for (int r = 0; r < n; ++r) link(group[r], mails, pptr, nzl, npad, ops);
+  for (int r = 0; r < n; ++r) link(group[r], mails, ops);
 }
 
 int micropp3x_slab_homogenize(micropp3x_slab *s, const double *eps, double *stress, int *out3) {

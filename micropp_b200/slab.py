@@ -96,15 +96,6 @@ def _bind(lib):
         "mgpu_fetch_stress": (None, [V, C.c_int, _ip, _dp]),
         "mgpu_dev_ptr": (V, [V, C.c_int]), "mgpu_stream": (V, [V]), "mgpu_implicit": (C.c_int, [V]),
         "mgpu_stage_get_u": (None, [V, C.c_int, _dp]),
-        # peer-memory exchange (NVLink P2P, no collective library inside the DPCG loop)
-        "mgpu_slab_mail": (V, [V]), "mgpu_ipc_export": (None, [V, C.c_char_p]),
-        "mgpu_ipc_open": (V, [C.c_int, C.c_char_p]), "mgpu_ipc_close": (None, [V]),
-        "mgpu_slab_link": (None, [V, C.c_int, C.c_int, C.POINTER(V), V, C.c_longlong, C.c_longlong, V, C.c_longlong,
-                                  C.c_longlong]),
-        "mgpu_slab_publish_p": (None, [V]), "mgpu_slab_halo_pull": (None, [V]), "mgpu_slab_post": (None, [V, C.c_int]),
-        "mgpu_slab_gather_tail": (None, [V, C.c_int, C.c_int, C.c_int, C.c_int]),
-        "mgpu_slab_error": (C.c_int, [V]), "mgpu_slab_cg_iteration": (None, [V, C.c_int, C.c_int]),
-        "mgpu_slab_cg_chunk": (None, [V, C.c_int, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -196,56 +187,20 @@ class SlabRVEPy:
             self.rbuf = [torch.empty(n3, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.exchanges = 0
         self.allreduces = 0
-        # DPCG operator: 3 = implicit operator of an all-elastic RVE (no assembled matrix), 0 = the slab's own ELL matrix
-        self.op = 3 if all(self.lib.mgpu_implicit(s.ctx) for s in self.slabs) else 0
-        # "peer": halo planes pulled from the neighbours' memory and dot products summed through peer-mapped
-        # mailboxes (NVLink P2P, device-side flags); "nccl": send/recv + all-reduce through torch.distributed
+        # DPCG operator: 3 = implicit operator of an all-elastic RVE (no assembled matrix), 0 = the slab's own ELL matrix;
+        # ONE operator for the whole RVE: every rank must take the same decision (all-reduce of the local flag)
+        imp = int(all(self.lib.mgpu_implicit(s.ctx) for s in self.slabs))
+        if world is not None:
+            t = torch.tensor([imp], dtype=torch.int32, device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            imp = int(t.item())
+        self.op = 3 if imp else 0
+        self.elastic = all(int(m[0]) == 0 for m in p["materials"][:3])
+        self.solves = 0
+        if exchange != "nccl":
+            raise ValueError("SlabRVEPy is the NCCL baseline transport; the peer-memory path is SlabRVE (C++ host)")
         self.exchange = exchange
         self._mapped = []
-        if exchange == "peer":
-            self._link_peers(device)
-
-    def _link_peers(self, device):
-        lib = self.lib
-        V = C.c_void_p
-        if self.world is None:   # every slab lives in this process: plain device pointers
-            mails = [lib.mgpu_slab_mail(s.ctx) for s in self.slabs]
-            pptr = [lib.mgpu_dev_ptr(s.ctx, 3) for s in self.slabs]
-            info = [(s.nzl, s.nn_pad) for s in self.slabs]
-            mine = range(len(self.slabs))
-        else:                    # one slab per process: CUDA IPC handles travel through the process group
-            s = self.slabs[0]
-            hm, hp = C.create_string_buffer(64), C.create_string_buffer(64)
-            lib.mgpu_ipc_export(lib.mgpu_slab_mail(s.ctx), hm)
-            lib.mgpu_ipc_export(lib.mgpu_dev_ptr(s.ctx, 3), hp)
-            allinfo = [None] * self.size
-            self.dist.all_gather_object(allinfo, (hm.raw, hp.raw, s.nzl, s.nn_pad))
-            mails, pptr, info = [], [], []
-            for r, (m_raw, p_raw, nzl, npad) in enumerate(allinfo):
-                info.append((nzl, npad))
-                if r == self.rank:
-                    mails.append(lib.mgpu_slab_mail(s.ctx))
-                    pptr.append(lib.mgpu_dev_ptr(s.ctx, 3))
-                    continue
-                mails.append(lib.mgpu_ipc_open(device, m_raw))
-                self._mapped.append(mails[-1])
-                if abs(r - self.rank) == 1:
-                    pptr.append(lib.mgpu_ipc_open(device, p_raw))
-                    self._mapped.append(pptr[-1])
-                else:
-                    pptr.append(None)
-            mine = [self.rank]
-        arr = (V * self.size)(*[V(m) for m in mails])
-        for i, r in enumerate(mine):
-            s = self.slabs[i]
-            lo = pptr[r - 1] if r > 0 else None
-            hi = pptr[r + 1] if r + 1 < self.size else None
-            lo_off = (info[r - 1][0] - 2) * s.nxny if r > 0 else 0          # the lower neighbour's top owned plane
-            hi_off = 1 * s.nxny if r + 1 < self.size else 0                  # the upper neighbour's bottom owned plane
-            lib.mgpu_slab_link(s.ctx, r, self.size, arr, lo, lo_off, info[r - 1][1] if r > 0 else 0, hi, hi_off,
-                               info[r + 1][1] if r + 1 < self.size else 0)
-        if self.world is not None:
-            self.dist.barrier()
 
     # ------------------------------------------------------------------ communication
     def _allreduce(self, k: int):
@@ -269,11 +224,6 @@ class SlabRVEPy:
         """Halo planes of p <- the neighbour's adjacent owned plane."""
         torch = self.torch
         self.exchanges += 1
-        if self.exchange == "peer":
-            if self.world is None:
-                torch.cuda.synchronize()   # one process, one stream per slab: the publishes must have run
-            self._each(self.lib.mgpu_slab_halo_pull)
-            return
         if self.world is None:
             torch.cuda.synchronize()
             for a, b in zip(self.slabs[:-1], self.slabs[1:]):  # a below b
@@ -300,43 +250,27 @@ class SlabRVEPy:
     def _reduced(self, kernel, kargs, k, tail_kind, tail_mode=0):
         """reducing kernel -> all-reduce of its k slab-local sums -> scalar tail on every slab"""
         self._each(kernel, *kargs)
-        if self.exchange == "peer":
-            self.allreduces += 1
-            self._each(self.lib.mgpu_slab_post, k)
-            if self.world is None:
-                self.torch.cuda.synchronize()   # all posts of this process's slabs before any tail waits for them
-            self._each(self.lib.mgpu_slab_gather_tail, self.L0, k, tail_kind, tail_mode)
-            return
         self._allreduce(k)
         self._each(self.lib.mgpu_tail, self.L0, 1, tail_kind, tail_mode)
 
     # ------------------------------------------------------------------ solver
     def cg_solve(self):
         lib, L0 = self.lib, self.L0
-        peer = self.exchange == "peer"
         self._reduced(lib.mgpu_cg_init, (L0, 1, self.op), 2, 1)
-        if peer:
-            self._each(lib.mgpu_slab_publish_p)
         while self.slabs[0].state().cg_active:
-            if peer and self.world is not None:
-                # one CUDA graph launch per chunk of iterations, nothing but kernels: the cross-rank steps (halo pull,
-                # rank-ordered sums) are device-side, their epochs live in the mailboxes
-                self.exchanges += self.cg_chunk
-                self.allreduces += 2 * self.cg_chunk
-                lib.mgpu_slab_cg_chunk(self.slabs[0].ctx, L0, self.op, self.cg_chunk)
-                continue
             for _ in range(self.cg_chunk):
                 self._exchange_p()
                 self._reduced(lib.mgpu_cg_spmv_dot, (L0, 1, self.op), 1, 2)
                 self._reduced(lib.mgpu_cg_update, (L0, 1), 2, 3)
                 self._each(lib.mgpu_cg_pupdate, L0, 1)
-                if peer:
-                    self._each(lib.mgpu_slab_publish_p)
         self._each(lib.mgpu_cg_finish, L0, 1)   # the deferred x += alpha p of the last iteration
 
     def homogenize(self, eps) -> dict:
         """set_displ_bc -> Newton-Raphson (src/solve.cpp:29-82) -> averaged stress (src/average.cpp:58-82)."""
         lib, L0 = self.lib, self.L0
+        if not self.elastic and self.solves > 0:
+            raise RuntimeError("the z-slab mode keeps no history: a non-elastic RVE can be solved once (virgin state)")
+        self.solves += 1
         e = np.ascontiguousarray(eps, dtype=np.float64)
         for s in self.slabs:
             lib.mgpu_set_slot_strain(s.ctx, 1, s.zero, e.ctypes.data_as(_dp))
@@ -375,16 +309,9 @@ class SlabRVEPy:
         self._each(self.lib.mgpu_sync)
 
     def peer_error(self) -> int:
-        """!= 0: a device-side wait for a peer timed out (peer exchange only)."""
-        return max(int(self.lib.mgpu_slab_error(s.ctx)) for s in self.slabs) if self.exchange == "peer" else 0
+        return 0
 
     def close(self):
-        if self.world is not None and self.exchange == "peer" and self.slabs:
-            self.sync()
-            self.dist.barrier()          # nobody unmaps memory a neighbour may still read
-        for m in self._mapped:
-            self.lib.mgpu_ipc_close(m)
-        self._mapped = []
         for s in self.slabs:
             s.close()
         self.slabs = []
@@ -393,8 +320,7 @@ class SlabRVEPy:
 # ------------------------------------------------------------------------------------------------ product path (C++ host)
 class SlabHandle(C.Structure):
     """micropp3x_slab_handle (include/micropp_b200_ext.h)."""
-    _fields_ = [("mail", C.c_char * 64), ("p", C.c_char * 64), ("nzl", C.c_longlong), ("nn_pad", C.c_longlong),
-                ("op", C.c_int), ("pad", C.c_int)]
+    _fields_ = [("mail", C.c_char * 64), ("op", C.c_int), ("pad", C.c_int)]
 
 
 def _bind_cxx(lib):
