@@ -418,7 +418,20 @@ def run_b200_workload(M, env: Env, name: str, ngp: int, steps: int, warmup: int,
     # roofline of the dominant kernel (rank 0's launches; every SpMV application of an RVE = one CG iteration)
     apps = float(np.sum(cost)) * steps
     imp_kernel = m.implicit_kernel()
+    hybrid = None
+    if imp_kernel < 0 and prof["hybrid_slot_apps"] > 0:
+        # RVEs with a damage / plastic phase: slots that are mostly inside their linear regime run the HYBRID operator
+        # (no matrix stream but for their listed rows); the roofline kernel stays the assembled k_spmv_dot of the other
+        # slots, counted with the applications the profiler itself saw
+        hybrid = {"rve_applications": prof["hybrid_slot_apps"], "kernel_ms": prof["hybrid_spmv_ms"],
+                  "share_of_applications": prof["hybrid_slot_apps"] / max(apps, 1.0),
+                  "share_of_step": prof["hybrid_spmv_ms"] / max(prof_dev_ms, 1e-9),
+                  "kernels": "k_spmv_dot_tmac + k_spmv_fix (implicit elastic row blocks, every node) + k_spmv_hyb "
+                             "(explicit rows of the nodes that touch a non-linear element)"}
+        apps = float(prof["spmv_slot_apps"])
     roof = spmv_roofline(name, n, prof, prof_dev_ms, apps, imp_kernel, steps)
+    if hybrid is not None:
+        roof["hybrid_operator"] = hybrid
 
     # all-elastic workloads: the same workload once more through the assembled-matrix path (MICROPP_IMPLICIT=0) on a
     # bounded batch, instrumented, so that the HBM-bound SpMV the north star names is measured in the same run

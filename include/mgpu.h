@@ -109,8 +109,8 @@ void mgpu_set_bc(mgpu_ctx *, int which_list, int n);
 void mgpu_asm_rhs(mgpu_ctx *, int which_list, int n, int mode);     /* mode 0: first of a Newton solve, 1: after update, 2: plain */
 void mgpu_asm_mat(mgpu_ctx *, int which_list, int n, int to_shared); /* to_shared: assemble slot list[0] into the shared A0 buffer */
 /* use_shared selects the operator of the solve: 0 the slot's own matrix, 1 the shared A0, 2 the generic host matrix,
-   3 the implicit operator of an all-elastic RVE (mgpu_implicit() != 0); mgpu_cg_update/pupdate follow the operator
-   of the last mgpu_cg_init */
+   3 the implicit operator of an all-elastic RVE (mgpu_implicit() != 0), 4 the hybrid operator (mgpu_hybrid_available());
+   mgpu_cg_update/pupdate follow the operator of the last mgpu_cg_init */
 /* host-only (no GPU): tiling of the implicit operator's TMA kernel for an nx x ny x nz RVE; see mgpu_kernels.cu */
 int mgpu_tmac_tiling_host(int nx, int ny, int nz, const int *elem_type, int *meta6, int *rowid, int *tiles4,
                           int *chunk_pure, int *fix_nodes2);
@@ -142,6 +142,16 @@ int mgpu_compact_range(mgpu_ctx *, int list_in, int off, int n_in, int list_out,
    CUDA graph over list 1 (the Newton list, whose device-side length mgpu_compact(.., 1, ..) maintains).  Returns
    the number of slots that need another step (syncs once). */
 int mgpu_newton_step_graph(mgpu_ctx *, int n_active, int use_shared);
+/* same on list set ls: 0 = lists 1 / 2 (as above), 1 = lists 6 / 7 (the hybrid-operator slots of mgpu_hybrid_split) */
+int mgpu_newton_step_graph_on(mgpu_ctx *, int ls, int n_active, int use_shared);
+
+/* ---- hybrid operator (use_shared = 4) of RVEs with a damage / plastic phase: implicit elastic row blocks for every node
+   whose 8 elements are inside their linear regime, explicit ELL rows only for the others ---- */
+int mgpu_hybrid_available(const mgpu_ctx *);
+/* probe the first n slots of list l at their current iterate, build the per-slot node lists, split: list 6 <- slots for
+   the hybrid operator, list 1 <- slots for the fully assembled one (l may be 1).  Syncs. */
+void mgpu_hybrid_split(mgpu_ctx *, int which_list, int n, int *n_hybrid, int *n_full);
+void mgpu_asm_mat_hyb(mgpu_ctx *, int which_list, int n); /* assembles the listed rows only */
 
 /* ---- slab mode (one RVE split in z-slabs over several GPUs): the caller all-reduces the slab-local sums between a
    reducing kernel and its scalar tail, and exchanges the halo planes of p before every SpMV ---- */
@@ -190,8 +200,9 @@ void mgpu_ell_cols(int nx, int ny, int nz, int *cols /* [3nn][81] */, int device
 /* ---- measurement ---- */
 void mgpu_prof_enable(mgpu_ctx *, int on);
 /* accumulated since last reset: [0]=spmv ms, [1]=spmv launches, [2]=spmv slot-applications, [3]=asm_mat ms,
-   [4]=asm_rhs ms, [5]=cg_update+pupdate ms */
-void mgpu_prof_read(mgpu_ctx *, double *out6, int reset);
+   [4]=asm_rhs ms, [5]=cg_update+pupdate ms, [6]=hybrid-operator spmv ms, [7]=its slot-applications ([0]..[2] then count
+   the other operators only) */
+void mgpu_prof_read(mgpu_ctx *, double *out8, int reset);
 void mgpu_timer_start(mgpu_ctx *);
 float mgpu_timer_stop(mgpu_ctx *); /* ms on the context stream (syncs) */
 /* isolated SpMV micro-benchmark on the first n slots of the pool (matrix contents as they are) */

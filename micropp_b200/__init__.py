@@ -119,7 +119,7 @@ def load():
         "micropp3x_elem_nodes": (None, [C.c_int] * 5 + [_ip]),
         "micropp3x_elem_colour": (C.c_int, [C.c_int] * 3),
         "micropp3x_prof_enable": (None, [H, C.c_int]),
-        "micropp3x_prof_read": (None, [H, _dp, C.c_int]),
+        "micropp3x_prof_read": (None, [H, _dp, C.c_int]), "micropp3x_hybrid_available": (C.c_int, [H]),
         "micropp3x_last_homogenize_ms": (C.c_double, [H]),
         "micropp3x_launch_count": (C.c_ulonglong, [H]),
         "micropp3x_bench_spmv": (C.c_double, [H, C.c_int, C.c_int]),
@@ -359,10 +359,15 @@ class Micropp3:
         self.lib.micropp3x_prof_enable(C.byref(self.h), int(bool(on)))
 
     def prof_read(self, reset=True):
-        out = np.zeros(6)
+        out = np.zeros(8)
         self.lib.micropp3x_prof_read(C.byref(self.h), _d(out), int(bool(reset)))
         return dict(spmv_ms=out[0], spmv_launches=int(out[1]), spmv_slot_apps=int(out[2]), asm_mat_ms=out[3],
-                    asm_rhs_ms=out[4], cg_vec_ms=out[5])
+                    asm_rhs_ms=out[4], cg_vec_ms=out[5], hybrid_spmv_ms=out[6], hybrid_slot_apps=int(out[7]))
+
+    def hybrid_available(self):
+        """True when RVEs with a damage / plastic phase may take the hybrid operator (implicit elastic row blocks +
+        explicit rows only where an element has left its linear regime)."""
+        return bool(self.lib.micropp3x_hybrid_available(C.byref(self.h)))
 
     def last_homogenize_ms(self):
         return float(self.lib.micropp3x_last_homogenize_ms(C.byref(self.h)))

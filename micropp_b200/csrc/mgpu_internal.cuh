@@ -39,7 +39,7 @@ constexpr int NPLANE = 243;  // 27 neighbours x 3 x 3
 // row blocks of the implicit operator: [27 neighbours][10] doubles, the 3x3 block of a neighbour in the first 9 --
 // 80-B groups are 16-B aligned, so a neighbour's block is five 128-bit loads (global or shared)
 constexpr int RB_NBR = 10, RB_LEN = 27 * RB_NBR;
-constexpr int NLIST = 6;
+constexpr int NLIST = 8;  // 0 caller, 1 Newton, 2 / 4 CG, 3 caller subset, 5 bench, 6 Newton (hybrid set), 7 CG (hybrid set)
 constexpr int NRED = 6;      // max values reduced per kernel
 
 struct MeshConst {
@@ -69,6 +69,12 @@ struct SlotTables {  // device arrays, one entry per slot
   double *partial; // [W][NRED][nblk_max]
   double *red;     // [W][8] slab-local sums handed to the all-reduce (slab mode)
   int nblk_max;
+  // hybrid operator (RVEs with a damage / plastic phase, see OP_HYBRID): per slot the elements that are past their
+  // material's linear regime, the interior nodes that touch one (compact list + inverse map) and their number
+  unsigned char *enl;  // [W][nelem_pad]
+  int *hnodes;         // [W][nint_pad]  interior-node indices, ascending
+  int *hpos;           // [W][nint_pad]  position in hnodes, or -1
+  int *hcnt;           // [W]
 };
 
 struct VecPool {
@@ -85,7 +91,9 @@ struct VecPool {
 };
 
 // operator selector of the DPCG kernels
-enum { OP_SLOT = 0, OP_SHARED = 1, OP_GENERIC = 2, OP_IMPLICIT = 3 };
+// OP_HYBRID: the implicit elastic row blocks for every node whose 8 elements are all in their linear regime, explicit
+// ELL rows (compact list, same plane-major tile layout) only for the nodes that touch a non-linear element
+enum { OP_SLOT = 0, OP_SHARED = 1, OP_GENERIC = 2, OP_IMPLICIT = 3, OP_HYBRID = 4 };
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -376,6 +384,9 @@ struct mgpu_ctx {
   int ngp = 0, W = 0;
   bool all_elastic = true;
   bool implicit = false;  // all-elastic RVE served by the implicit operator (no per-slot matrices)
+  bool hybrid = false;    // RVE with a damage / plastic phase: implicit tables built too, OP_HYBRID available
+  int hyb_max = 0;        // a slot takes the hybrid operator while its node list holds at most this many rows
+  bool defer_fold = false;  // launch_imp_spmv leaves the p.Ap fold to the caller (hybrid SpMV adds its correction first)
   int mat_slots = 0;      // slots of the explicit matrix pool
   int cg_op = mgpu_int::OP_SLOT;    // operator of the DPCG solve in flight (set by mgpu_cg_init)
   int nrows = 0;
@@ -409,8 +420,9 @@ struct mgpu_ctx {
   int ctan_chunk = 0;
   mgpu_int::VecPool V{};
   mgpu_int::SlotTables T{};
-  int *d_list[mgpu_int::NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int *d_list[mgpu_int::NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int *d_count = nullptr;
+  unsigned long long *d_apps = nullptr;  // [8] DPCG iterations done per operator (measurement)
   int *d_cnt2 = nullptr;           // device-side list lengths used inside graphs: [0] Newton list, [1] CG list
   const int *dyn_count = nullptr;  // non-null while a graph is being captured: launches test it per block
   int *h_count = nullptr;  // pinned
@@ -434,14 +446,14 @@ struct mgpu_ctx {
     int slots;
   };
   std::vector<EvPair> ev_live, ev_pool;
-  double prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  double prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   unsigned long long launches = 0;
   struct StepGraph {
     cudaGraphExec_t exec;
     int fixed_launches, body_launches;
   };
-  std::map<long long, StepGraph> step_graphs;  // key = bucket * 4 + operator
+  std::map<long long, StepGraph> step_graphs;  // key = (bucket * 8 + operator) * 2 + list set
 };
 
 namespace mgpu_int {
@@ -493,6 +505,7 @@ void implicit_destroy(mgpu_ctx *c);
 // Ap = A p (+ per-slot p.Ap and its scalar tail) over the first n entries of list l; kern: the context's kernel
 // (c->imp_kernel) or an explicit IMP_* id (parity tests / A-B measurements); force: apply to inactive slots too
 void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern);
+void launch_fold_spmv(mgpu_ctx *c, int l, int n, int nfold, int force);
 void build_row_blocks(mgpu_ctx *c, const std::vector<int> &codes);  // mgpu_kernels.cu (k_rows_build)
 enum { IMP_SIMPLE = 0, IMP_TMAC = 3 };
 

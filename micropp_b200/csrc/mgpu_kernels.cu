@@ -310,7 +310,7 @@ constexpr int CTAN_LEN = 8 * 36;  // doubles per element in the tangent scratch
 __global__ void __launch_bounds__(NT)
     k_elem_ctan(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                 const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
-                double *__restrict__ cbuf, size_t cstride) {
+                double *__restrict__ cbuf, size_t cstride, int hybrid) {
   const int slot = slot_of(L);
   if (slot < 0) return;
   const double *u = u_pool + (size_t)slot * vstride;
@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(NT)
   const int type = __ldg(&elem_type[e]);
   const mpp_material m = P.mat[type];
   if (m.type == MPP_ELASTIC) return;  // rows come from the per-material table
+  // hybrid operator: elements inside their linear regime take the rows of their material's elastic law too
+  if (hybrid && !T.enl[(size_t)slot * P.nelem_pad + e]) return;
   const int ez = e / (P.nex * P.ney);
   const int r = e - ez * P.nex * P.ney;
   const int ey = r / P.nex, ex = r - ey * P.nex;
@@ -341,23 +343,30 @@ __global__ void __launch_bounds__(NT)
 __global__ void __launch_bounds__(NT)
     k_asm_mat_general(const __grid_constant__ MeshConst P, const Lst L, double *mat_pool,
                       size_t mstride, double *mat_shared, const int *__restrict__ elem_type,
-                      const double *__restrict__ ke_tab, const double *__restrict__ cbuf, size_t cstride) {
+                      const double *__restrict__ ke_tab, const double *__restrict__ cbuf, size_t cstride,
+                      SlotTables T, int hybrid) {
   extern __shared__ double s_acc[];  // [GN][243]
   const int slot = slot_of(L);
   if (slot < 0) return;
   const double *cb = cbuf + (size_t)blockIdx.y * cstride;
   double *A = mat_shared ? mat_shared : mat_pool + (size_t)slot * mstride;
+  // hybrid operator: only the rows of the slot's compact node list are assembled (row of list position q at tile
+  // position q); elements in their linear regime contribute the rows of their elastic law
+  const int nrows_out = hybrid ? T.hcnt[slot] : P.nint;
+  if ((int)blockIdx.x * GN >= nrows_out) return;
+  const int *hnodes = hybrid ? T.hnodes + (size_t)slot * P.nint_pad : nullptr;
+  const unsigned char *enl = hybrid ? T.enl + (size_t)slot * P.nelem_pad : nullptr;
 
-  for (int q = threadIdx.x; q < GN * NPLANE; q += NT) s_acc[q] = 0.0;
+  for (int t = threadIdx.x; t < GN * NPLANE; t += NT) s_acc[t] = 0.0;
   __syncthreads();
 
   // element-major thread order: the 16 lanes of a half-warp hold the SAME corner element of 16 x-consecutive nodes,
   // i.e. 16 consecutive elements => their tangent loads are 128-B segments (node-major order: 8 segments of 32 B)
   const int ln = threadIdx.x % GN, c = threadIdx.x / GN;
-  const int m = blockIdx.x * GN + ln;  // interior-node index
+  const int q = blockIdx.x * GN + ln;  // row position (= interior-node index unless a node list is given)
   int i = 0, j = 0, k = 0;
-  const bool work = m < P.nint;
-  if (work) interior_node(P, m, i, j, k);
+  const bool work = q < nrows_out;
+  if (work) interior_node(P, hnodes ? hnodes[q] : q, i, j, k);
 
   double R[72];
   int a = 0;
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(NT)
     a = corner_of(1 - ax, 1 - ay, 1 - az);
     const int e = (ez * P.ney + ey) * P.nex + ex;
     const int type = __ldg(&elem_type[e]);
-    if (P.mat[type].type == MPP_ELASTIC) {
+    if (P.mat[type].type == MPP_ELASTIC || (enl && !enl[e])) {
       const double *ke = ke_tab + type * 576 + a * 72;
 #pragma unroll
       for (int q = 0; q < 72; ++q) R[q] = __ldg(&ke[q]);
@@ -423,11 +432,100 @@ __global__ void __launch_bounds__(NT)
     }
     __syncthreads();
   }
-  for (int q = threadIdx.x; q < GN * NPLANE; q += NT) {
-    const int pl = q / GN, l = q % GN;
+  for (int t = threadIdx.x; t < GN * NPLANE; t += NT) {
+    const int pl = t / GN, l = t % GN;
     const int md = blockIdx.x * GN + l;
-    if (md < P.nint) A[aidx(pl, md)] = s_acc[l * NPLANE + pl];
+    if (md < nrows_out) A[aidx(pl, md)] = s_acc[l * NPLANE + pl];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hybrid operator of RVEs with a damage / plastic phase (OP_HYBRID).
+//
+// The Jacobian row of an interior node depends on u only through the elements around it that are PAST their material's
+// linear regime; everywhere else it is the row of the elastic law -- for an elastic element by definition, for a damage
+// / plastic element below its threshold because the reference's forward-difference tangent of a linear stress is the
+// elastic tangent up to a rounding residue of about 2e-10 (src/material.cpp:49-63).  Measured on the damage50 load path
+// (profiles/r03a_damage_fraction.log): until a Gauss point's matrix phase crosses the threshold as a whole, 0 .. 12 %
+// of its rows touch a non-linear element.  So: (1) k_probe_lin flags the non-linear elements of every slot at the
+// current iterate, (2) k_hyb_list turns them into the compact list of interior nodes that touch one, (3) only those
+// rows are assembled (k_elem_ctan / k_asm_mat_general on the list) into the slot's matrix buffer, (4) the SpMV is the
+// implicit elastic operator for ALL nodes followed by k_spmv_hyb, which overwrites the listed nodes with their
+// explicit rows and corrects p.Ap.  Slots whose list exceeds MICROPP_HYBRID_MAX (default 0.7) of the rows take the
+// fully assembled path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+    k_probe_lin(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, const double *__restrict__ u_pool,
+                size_t vstride, const int *__restrict__ elem_type) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  const int e = blockIdx.x * NT + threadIdx.x;
+  if (e >= P.nelem) return;
+  const mpp_material m = P.mat[__ldg(&elem_type[e])];
+  bool nl = false;
+  if (m.type != MPP_ELASTIC) {
+    const double *u = u_pool + (size_t)slot * vstride;
+    const double *vars = T.vars_old[slot];
+    const int ez = e / (P.nex * P.ney);
+    const int r = e - ez * P.nex * P.ney;
+    const int ey = r / P.nex, ex = r - ey * P.nex;
+    double ue[24];
+    gather_ue(P, u, ex, ey, ez, ue);
+    const int nv = mat_nvar(m.type);
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+      double eps[6], vbuf[7];
+      gp_strain(P.dsh[gp], ue, eps);
+      const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+      // past the threshold now (evolute's own test), or carrying damage from before (stress = (1 - D_old) sigma_lin:
+      // not the elastic tangent even while unloading)
+      nl |= mat_evolute(m, eps, v, nullptr);
+      if (m.type == MPP_DAMAGE && v && v[1] != 0.0) nl = true;
+    }
+  }
+  T.enl[(size_t)slot * P.nelem_pad + e] = nl ? 1 : 0;
+}
+
+// one block per slot: interior nodes that touch a flagged element -> ascending compact list + inverse map + count
+__global__ void __launch_bounds__(1024) k_hyb_list(const __grid_constant__ MeshConst P, const Lst L, SlotTables T) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const unsigned char *enl = T.enl + (size_t)slot * P.nelem_pad;
+  int *hnodes = T.hnodes + (size_t)slot * P.nint_pad, *hpos = T.hpos + (size_t)slot * P.nint_pad;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int start = 0; start < P.nint; start += 1024) {
+    const int m = start + threadIdx.x;
+    int flag = 0;
+    if (m < P.nint) {
+      int i, j, k;
+      interior_node(P, m, i, j, k);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        flag |= enl[((k - 1 + (c & 1)) * P.ney + (j - 1 + ((c >> 1) & 1))) * P.nex + (i - 1 + ((c >> 2) & 1))];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int ww = 0; ww < w; ++ww) off += s_warp[ww];
+    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+    if (m < P.nint) {
+      hpos[m] = flag ? pos : -1;
+      if (flag) hnodes[pos] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int ww = 0; ww < 32; ++ww) tot += s_warp[ww];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) T.hcnt[slot] = s_base;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,12 +553,17 @@ __global__ void __launch_bounds__(NT)
     for (int d = 0; d < 3; ++d) {
       const size_t ix = vo + (size_t)d * P.nn_pad + n;
       double diag = 1.0;  // boundary rows are identity rows (ell_set_bc_3D)
+      // hybrid: the explicit row of a listed node, the row-block table for every other node
+      const int hq = (use_shared == OP_HYBRID && !bnd) ? T.hpos[(size_t)slot * P.nint_pad + m] : -1;
       if (use_shared == OP_GENERIC)
         diag = V.gen[((size_t)n * 3 + d) * 81 + 13 * 3 + d];
-      else if (use_shared != OP_IMPLICIT && !bnd)
+      else if (use_shared == OP_HYBRID) {
+        if (hq >= 0) diag = A[aidx(13 * 9 + d * 4, hq)];
+      } else if (use_shared != OP_IMPLICIT && !bnd)
         diag = A[aidx(13 * 9 + d * 4, m)];
       // src/ell.cpp:73-76 (the implicit operator keeps 1/diag per distinct row block)
-      const double kk = (use_shared == OP_IMPLICIT && !bnd) ? __ldg(&V.rkinv[__ldg(&V.rowid[m]) * 3 + d]) : 1 / diag;
+      const bool table = !bnd && (use_shared == OP_IMPLICIT || (use_shared == OP_HYBRID && hq < 0));
+      const double kk = table ? __ldg(&V.rkinv[__ldg(&V.rowid[m]) * 3 + d]) : 1 / diag;
       const double r = V.b[ix];    // r = b - A*0 (src/ell.cpp:78-82)
       const double z = kk * r;
       if (use_shared != OP_IMPLICIT) {  // the implicit operator re-derives k (and z = k r) from its row table
@@ -583,6 +686,38 @@ __device__ __forceinline__ double imp_kk(const MeshConst &P, const VecPool &V, i
   if (on_boundary(P, i, j, k)) return 1.0;  // 1 / 1
   const int m = interior_index(P, i, j, k);
   return __ldg(&V.rkinv[__ldg(&V.rowid[m]) * 3 + d]);
+}
+
+// Hybrid SpMV, second half: the implicit elastic operator has produced Ap for every interior node; the nodes of the
+// slot's list get their explicit row instead (same value order as k_spmv_dot: tile position = list position), and the
+// per-block partial sums carry the CORRECTION p.(Ap_explicit - Ap_elastic) so that the fold of all partials is p.Ap.
+__global__ void __launch_bounds__(NT)
+    k_spmv_hyb(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int pbase, int force) {
+  __shared__ double sm[NRED * (NT / 32)];
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (!force && !st->cg_active) return;
+  const double *A = V.mat + (size_t)slot * V.mstride;
+  const size_t vo = (size_t)slot * V.vstride;
+  const double *p = V.p + vo;
+  double *Ap = V.Ap + vo;
+  const int q = blockIdx.x * NT + threadIdx.x;
+  double red[1] = {0.0};
+  if (q < T.hcnt[slot]) {
+    int i, j, k;
+    const int n = interior_node(P, T.hnodes[(size_t)slot * P.nint_pad + q], i, j, k);
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    const size_t npad = P.nn_pad;
+    SpmvLoop<0>::run(A + aidx(0, q), p, npad, n, P.nx, P.nxny, y0, y1, y2);
+    const double o0 = Ap[n], o1 = Ap[npad + n], o2 = Ap[2 * npad + n];
+    Ap[n] = y0;
+    Ap[npad + n] = y1;
+    Ap[2 * npad + n] = y2;
+    red[0] = p[n] * (y0 - o0) + p[npad + n] * (y1 - o1) + p[2 * npad + n] * (y2 - o2);
+  }
+  block_sum<1>(red, sm);
+  if (threadIdx.x == 0) T.partial[((size_t)slot * NRED + FOLD_PLANE) * T.nblk_max + pbase + blockIdx.x] = red[0];
 }
 
 // cg_update / cg_pupdate of the implicit operator: k = 1/diag comes from the row table and z = k r is recomputed
@@ -865,14 +1000,17 @@ __global__ void __launch_bounds__(NT)
 
 // u += du (src/solve.cpp:73) and newton.solver_its += cg_its (src/solve.cpp:71)
 __global__ void __launch_bounds__(NT)
-    k_axpy_u(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V) {
+    k_axpy_u(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, unsigned long long *apps) {
   const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
   if (!st->nr_active) return;
   const size_t vo = (size_t)slot * V.vstride;
   const int n = blockIdx.x * NT + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) st->solver_its += st->cg_its;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->solver_its += st->cg_its;
+    atomicAdd(apps, (unsigned long long)st->cg_its);  // operator applications of this solve (measurement)
+  }
   if (n >= P.nn) return;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -1203,7 +1341,8 @@ __global__ void k_clear_nl(const int *__restrict__ list, int n, SlotTables T) {
 // allowed: every entry of a chunk is read before the barrier that precedes the chunk's writes, and writes never
 // run ahead of reads.
 __global__ void k_compact(const int *in, int n_in, const int *n_in_dev, int *out, int *count, int *count2,
-                          SlotTables T, int mode, cudaGraphConditionalHandle cond, int cond_set, int *trips) {
+                          SlotTables T, int mode, cudaGraphConditionalHandle cond, int cond_set, int *trips,
+                          int hyb_max = 0) {
   if (n_in_dev) n_in = *n_in_dev;
   __shared__ int s_warp[32];
   __shared__ int s_base;
@@ -1216,7 +1355,11 @@ __global__ void k_compact(const int *in, int n_in, const int *n_in_dev, int *out
     if (i < n_in) {
       slot = in[i];
       const mgpu_slot_state *st = &T.state[slot];
-      keep = mode ? st->cg_active : st->nr_active;
+      // 0: Newton-active, 1: CG-active, 2 / 3: Newton-active slots for the hybrid / the fully assembled operator
+      if (mode <= 1)
+        keep = mode ? st->cg_active : st->nr_active;
+      else
+        keep = st->nr_active && ((T.hcnt[slot] <= hyb_max) == (mode == 2));
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_warp[w] = __popc(bal);
@@ -1281,6 +1424,10 @@ void prof_drain(mgpu_ctx *c) {
       case 1: c->prof_acc[3] += ms; break;
       case 2: c->prof_acc[4] += ms; break;
       case 3: c->prof_acc[5] += ms; break;
+      case 4:  // hybrid SpMV (implicit operator + explicit rows of the listed nodes)
+        c->prof_acc[6] += ms;
+        c->prof_acc[7] += e.slots;
+        break;
       default: break;
     }
     c->ev_pool.push_back(e);
@@ -1493,8 +1640,18 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   const size_t mlen = (size_t)NPLANE * P.nint_pad;
   int nblk_max = std::max((P.nn + NT - 1) / NT, (P.nelem + NT - 1) / NT);
   c->implicit = c->all_elastic && cfg->implicit_elastic && P.nint > 0;
-  const size_t per_slot =
-      sizeof(double) * ((c->implicit ? 0 : mlen) + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256;
+  // RVE with a damage / plastic phase: the implicit tables are built as well (elastic law of every material) and the
+  // hybrid operator serves the slots that are mostly inside their linear regime.  Needs the TMA kernel (nx even).
+  c->hybrid = !c->all_elastic && cfg->implicit_elastic && !cfg->slab && P.nint > 0 && P.nx % 2 == 0;
+  if (const char *env = getenv("MICROPP_HYBRID")) c->hybrid = c->hybrid && atoi(env) != 0;
+  {
+    double frac = 0.7;
+    if (const char *env = getenv("MICROPP_HYBRID_MAX")) frac = atof(env);
+    c->hyb_max = (int)(frac * P.nint);
+  }
+  if (c->hybrid) nblk_max += (P.nint + NT - 1) / NT;  // partial sums of k_spmv_hyb behind those of the implicit SpMV
+  const size_t per_slot = sizeof(double) * ((c->implicit ? 0 : mlen) + 8 * vlen + (size_t)NRED * nblk_max + 12) + 256 +
+                          (c->hybrid ? (size_t)P.nelem_pad + 8 * (size_t)P.nint_pad : 0);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   size_t reserve = sizeof(double) * mlen * (c->implicit ? 3 : 1) /* A0 (+ 2 explicit slots) */ + (size_t(1) << 30);
@@ -1551,7 +1708,10 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
 
   // implicit operator: row-block table, tilings and TMA descriptors of the SpMV kernels (spmv_implicit.cu); may raise
   // nblk_max (the per-slot partial-sum buffer also holds the per-(item, warp) partials of p.Ap)
-  if (c->implicit) implicit_setup(c, cfg, &nblk_max);
+  if (c->implicit || c->hybrid) {
+    implicit_setup(c, cfg, &nblk_max);
+    if (c->hybrid && c->imp_kernel != IMP_TMAC) c->hybrid = false;
+  }
 
   SlotTables &T = c->T;
   T.nblk_max = nblk_max;
@@ -1568,11 +1728,22 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
   CK(cudaMalloc(&T.partial, sizeof(double) * (size_t)NRED * nblk_max * W));
   CK(cudaMalloc(&T.red, sizeof(double) * 8 * W));
   CK(cudaMemset(T.red, 0, sizeof(double) * 8 * W));
+  T.enl = nullptr;
+  T.hnodes = T.hpos = T.hcnt = nullptr;
+  if (c->hybrid) {
+    CK(cudaMalloc(&T.enl, (size_t)P.nelem_pad * W));
+    CK(cudaMalloc(&T.hnodes, sizeof(int) * (size_t)P.nint_pad * W));
+    CK(cudaMalloc(&T.hpos, sizeof(int) * (size_t)P.nint_pad * W));
+    CK(cudaMalloc(&T.hcnt, sizeof(int) * W));
+    CK(cudaMemset(T.hcnt, 0, sizeof(int) * W));
+  }
   for (int l = 0; l < NLIST; ++l) CK(cudaMalloc(&c->d_list[l], sizeof(int) * W));
   CK(cudaMalloc(&c->d_count, sizeof(int)));
-  CK(cudaMallocHost(&c->h_count, 4 * sizeof(int)));
-  CK(cudaMalloc(&c->d_cnt2, 4 * sizeof(int)));
-  CK(cudaMemset(c->d_cnt2, 0, 4 * sizeof(int)));
+  CK(cudaMallocHost(&c->h_count, 8 * sizeof(int)));
+  CK(cudaMalloc(&c->d_apps, 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_apps, 0, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_cnt2, 8 * sizeof(int)));
+  CK(cudaMemset(c->d_cnt2, 0, 8 * sizeof(int)));
 
   c->slot_gp.assign(W, -1);
   c->h_vars_old.assign(W, nullptr);
@@ -1613,10 +1784,15 @@ void mgpu_destroy(mgpu_ctx *c) {
   cudaFree(c->T.stress);
   cudaFree(c->T.partial);
   cudaFree(c->T.red);
+  if (c->T.enl) cudaFree(c->T.enl);
+  if (c->T.hnodes) cudaFree(c->T.hnodes);
+  if (c->T.hpos) cudaFree(c->T.hpos);
+  if (c->T.hcnt) cudaFree(c->T.hcnt);
   for (int l = 0; l < NLIST; ++l) cudaFree(c->d_list[l]);
   cudaFree(c->d_count);
   cudaFreeHost(c->h_count);
   cudaFree(c->d_cnt2);
+  cudaFree(c->d_apps);
   for (auto &kv : c->step_graphs) cudaGraphExecDestroy(kv.second.exec);
   cudaFree(c->d_elem_type);
   cudaFree(c->d_ke);
@@ -1787,7 +1963,11 @@ void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
   }
   CK(cudaGetLastError());
 }
-void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
+static void asm_mat_impl(mgpu_ctx *c, int l, int n, int to_shared, int hybrid);
+void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) { asm_mat_impl(c, l, n, to_shared, 0); }
+// hybrid operator: only the rows of every slot's node list (mgpu_hybrid_split)
+void mgpu_asm_mat_hyb(mgpu_ctx *c, int l, int n) { asm_mat_impl(c, l, n, 0, 1); }
+static void asm_mat_impl(mgpu_ctx *c, int l, int n, int to_shared, int hybrid) {
   if (n <= 0) return;
   double *shared = nullptr;
   if (to_shared) {
@@ -1813,10 +1993,10 @@ void mgpu_asm_mat(mgpu_ctx *c, int l, int n, int to_shared) {
       const int cnt = std::min(c->ctan_chunk, n - off);
       const Lst lst = lst_of(c, l, off);
       k_elem_ctan<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
-                                                          c->d_ctan, cstride);
+                                                          c->d_ctan, cstride, hybrid);
       dim3 g(std::max((c->mc.nint + GN - 1) / GN, 1), cnt);
       k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
-          c->mc, lst, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke, c->d_ctan, cstride);
+          c->mc, lst, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke, c->d_ctan, cstride, c->T, hybrid);
       c->launches += 1;
     }
   }
@@ -1839,8 +2019,8 @@ static void require_mat_pool(const mgpu_ctx *c, int n, int op, const char *who) 
 void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   require_mat_pool(c, n, use_shared, "mgpu_cg_init");
-  if (use_shared == OP_IMPLICIT && !c->implicit) {
-    fprintf(stderr, "micropp-b200: implicit operator requested for an RVE that is not all-elastic\n");
+  if ((use_shared == OP_IMPLICIT && !c->implicit) || (use_shared == OP_HYBRID && !c->hybrid)) {
+    fprintf(stderr, "micropp-b200: operator %d requested on a context that does not provide it\n", use_shared);
     abort();
   }
   c->cg_op = use_shared;
@@ -1851,9 +2031,18 @@ void mgpu_cg_init(mgpu_ctx *c, int l, int n, int use_shared) {
 void mgpu_cg_spmv_dot(mgpu_ctx *c, int l, int n, int use_shared) {
   if (n <= 0) return;
   require_mat_pool(c, n, use_shared, "mgpu_cg_spmv_dot");
-  ProfScope ps(c, 0, n);
+  ProfScope ps(c, use_shared == OP_HYBRID ? 4 : 0, n);
   if (use_shared == OP_IMPLICIT) {
     launch_imp_spmv(c, l, n, 0, c->imp_kernel);
+  } else if (use_shared == OP_HYBRID) {
+    // the implicit elastic operator on every node, then the explicit rows of the listed nodes + the p.Ap correction
+    c->defer_fold = true;
+    launch_imp_spmv(c, l, n, 0, c->imp_kernel);
+    c->defer_fold = false;
+    const dim3 g = int_grid(c, n);
+    k_spmv_hyb<<<g, NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, c->last_spmv_nfold, 0);
+    launch_fold_spmv(c, l, n, c->last_spmv_nfold + (int)g.x, 0);
+    c->launches += 2;
   } else {
     c->last_spmv_nfold = 0;
     k_spmv_dot<<<int_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, use_shared, 0);
@@ -1894,7 +2083,7 @@ void mgpu_cg_finish(mgpu_ctx *c, int l, int n) {
 void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V);
+  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, c->d_apps + (c->cg_op & 7));
   CK(cudaGetLastError());
 }
 void mgpu_ave_stress(mgpu_ctx *c, int l, int n) {
@@ -1940,7 +2129,9 @@ int mgpu_compact_range(mgpu_ctx *c, int list_in, int off, int n_in, int list_out
   if (n_in <= 0) return 0;
   c->launches++;
   // lists 1 (Newton) and 2 (CG) keep their length on the device too: the step graphs start from it
-  int *count2 = list_out == 1 ? c->d_cnt2 : (list_out == 2 ? c->d_cnt2 + 1 : nullptr);
+  // lists 1 / 6 (Newton) and 2 / 7 (CG) keep their length on the device too: the step graphs start from it
+  int *count2 = list_out == 1 ? c->d_cnt2 : list_out == 2 ? c->d_cnt2 + 1 : list_out == 6 ? c->d_cnt2 + 4 :
+                list_out == 7 ? c->d_cnt2 + 5 : nullptr;
   k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[list_in] + off, n_in, nullptr, c->d_list[list_out], c->d_count, count2,
                                        c->T, mode, cudaGraphConditionalHandle(), 0, nullptr);
   CK(cudaGetLastError());
@@ -1973,7 +2164,10 @@ std::vector<cudaGraphNode_t> capture_end(mgpu_ctx *c) {
   return out;
 }
 
-mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
+mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared, int ls) {
+  // list set: 0 = lists 1 (Newton) / 2 (CG) with counters d_cnt2[0..2], 1 = lists 6 / 7 with d_cnt2[4..6]
+  const int LN = ls ? 6 : 1, LC = ls ? 7 : 2;
+  int *cnt = c->d_cnt2 + 4 * ls;
   const bool prof = c->prof;
   c->prof = false;  // no event records inside a capture
   const unsigned long long l0 = c->launches;
@@ -1984,11 +2178,12 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
 
   // head: Jacobian, CG start, CG list := Newton-list slots whose loop-head test says "iterate"
   capture_begin(c, g, nullptr, 0);
-  c->dyn_count = c->d_cnt2;
-  if (use_shared == OP_SLOT) mgpu_asm_mat(c, 1, B, 0);
-  mgpu_cg_init(c, 1, B, use_shared);
-  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[2], c->d_cnt2 + 1, nullptr, c->T, 1, cond,
-                                       1, nullptr);
+  c->dyn_count = cnt;
+  if (use_shared == OP_SLOT) mgpu_asm_mat(c, LN, B, 0);
+  if (use_shared == OP_HYBRID) mgpu_asm_mat_hyb(c, LN, B);
+  mgpu_cg_init(c, LN, B, use_shared);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[LN], 0, cnt, c->d_list[LC], cnt + 1, nullptr, c->T, 1, cond, 1,
+                                       nullptr);
   c->launches++;
   std::vector<cudaGraphNode_t> leaves = capture_end(c);
   const int head = (int)(c->launches - l0);
@@ -2004,12 +2199,12 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
   cudaGraph_t body = wp.conditional.phGraph_out[0];
   const unsigned long long l1 = c->launches;
   capture_begin(c, body, nullptr, 0);
-  c->dyn_count = c->d_cnt2 + 1;
-  mgpu_cg_spmv_dot(c, 2, B, use_shared);
-  mgpu_cg_update(c, 2, B);
-  mgpu_cg_pupdate(c, 2, B);
-  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[2], 0, c->d_cnt2 + 1, c->d_list[2], c->d_cnt2 + 1, nullptr, c->T, 1,
-                                       cond, 1, c->d_cnt2 + 2);
+  c->dyn_count = cnt + 1;
+  mgpu_cg_spmv_dot(c, LC, B, use_shared);
+  mgpu_cg_update(c, LC, B);
+  mgpu_cg_pupdate(c, LC, B);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[LC], 0, cnt + 1, c->d_list[LC], cnt + 1, nullptr, c->T, 1, cond, 1,
+                                       cnt + 2);
   c->launches++;
   capture_end(c);
   const int body_l = (int)(c->launches - l1);
@@ -2017,14 +2212,13 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
   // tail: update, residual + Newton test, Newton list compaction, list lengths to the host
   const unsigned long long l2 = c->launches;
   capture_begin(c, g, &wnode, 1);
-  c->dyn_count = c->d_cnt2;
-  mgpu_cg_finish(c, 1, B);
-  mgpu_axpy_u(c, 1, B);
-  mgpu_asm_rhs(c, 1, B, 1);
-  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[1], 0, c->d_cnt2, c->d_list[1], c->d_cnt2, nullptr, c->T, 0, cond, 0,
-                                       nullptr);
+  c->dyn_count = cnt;
+  mgpu_cg_finish(c, LN, B);
+  mgpu_axpy_u(c, LN, B);
+  mgpu_asm_rhs(c, LN, B, 1);
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[LN], 0, cnt, c->d_list[LN], cnt, nullptr, c->T, 0, cond, 0, nullptr);
   c->launches++;
-  CK(cudaMemcpyAsync(c->h_count, c->d_cnt2, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_count + 4 * ls, cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   capture_end(c);
   const int tail = (int)(c->launches - l2);
   c->dyn_count = nullptr;
@@ -2041,20 +2235,50 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared) {
 
 }  // namespace
 
-extern "C" int mgpu_newton_step_graph(mgpu_ctx *c, int n_active, int use_shared) {
+extern "C" int mgpu_newton_step_graph_on(mgpu_ctx *c, int ls, int n_active, int use_shared) {
   if (n_active <= 0) return 0;
   CK(cudaSetDevice(c->device));
   int B = 1;
   while (B < n_active) B <<= 1;
   B = std::min(B, c->W);
-  const long long key = (long long)B * 4 + use_shared;
+  const long long key = ((long long)B * 8 + use_shared) * 2 + ls;
   auto it = c->step_graphs.find(key);
-  if (it == c->step_graphs.end()) it = c->step_graphs.emplace(key, build_step_graph(c, B, use_shared)).first;
-  CK(cudaMemsetAsync(c->d_cnt2 + 2, 0, sizeof(int), c->stream));
+  if (it == c->step_graphs.end()) it = c->step_graphs.emplace(key, build_step_graph(c, B, use_shared, ls)).first;
+  CK(cudaMemsetAsync(c->d_cnt2 + 4 * ls + 2, 0, sizeof(int), c->stream));
   CK(cudaGraphLaunch(it->second.exec, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->launches += it->second.fixed_launches + (unsigned long long)it->second.body_launches * c->h_count[2];
-  return c->h_count[0];
+  c->launches += it->second.fixed_launches + (unsigned long long)it->second.body_launches * c->h_count[4 * ls + 2];
+  return c->h_count[4 * ls];
+}
+extern "C" int mgpu_newton_step_graph(mgpu_ctx *c, int n_active, int use_shared) {
+  return mgpu_newton_step_graph_on(c, 0, n_active, use_shared);
+}
+
+// ---- hybrid operator: probe + split ------------------------------------------------------------------------
+extern "C" int mgpu_hybrid_available(const mgpu_ctx *c) { return c->hybrid ? 1 : 0; }
+// Flags the non-linear elements of the first n slots of list l at their current iterate, builds the per-slot node
+// lists, and splits the slots into list 6 (hybrid operator: at most hyb_max listed rows) and list 1 (fully assembled
+// operator).  l may be 1 (compacted in place).  Syncs.
+extern "C" void mgpu_hybrid_split(mgpu_ctx *c, int l, int n, int *n_hybrid, int *n_full) {
+  *n_hybrid = *n_full = 0;
+  if (n <= 0) return;
+  CK(cudaSetDevice(c->device));
+  {
+    ProfScope ps(c, 1, n);
+    k_probe_lin<<<elem_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V.u, c->V.vstride, c->d_elem_type);
+    k_hyb_list<<<dim3(1, n), 1024, 0, c->stream>>>(c->mc, lst_of(c, l), c->T);
+  }
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[l], n, nullptr, c->d_list[6], c->d_count, c->d_cnt2 + 4, c->T, 2,
+                                       cudaGraphConditionalHandle(), 0, nullptr, c->hyb_max);
+  CK(cudaMemcpyAsync(c->h_count + 3, c->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[l], n, nullptr, c->d_list[1], c->d_count, c->d_cnt2, c->T, 3,
+                                       cudaGraphConditionalHandle(), 0, nullptr, c->hyb_max);
+  CK(cudaMemcpyAsync(c->h_count + 7, c->d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches += 3;
+  *n_hybrid = c->h_count[3];
+  *n_full = c->h_count[7];
 }
 
 // ---- slab mode ---------------------------------------------------------------------------------
@@ -2349,11 +2573,21 @@ void mgpu_prof_enable(mgpu_ctx *c, int on) {
   prof_drain(c);
   c->prof = on != 0;
 }
-void mgpu_prof_read(mgpu_ctx *c, double *out6, int reset) {
+void mgpu_prof_read(mgpu_ctx *c, double *out8, int reset) {
   prof_drain(c);
-  for (int i = 0; i < 6; ++i) out6[i] = c->prof_acc[i];
+  for (int i = 0; i < 8; ++i) out8[i] = c->prof_acc[i];
+  // RVE applications of the operators, counted on the device (the DPCG iterations every slot really did)
+  unsigned long long apps[8];
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(apps, c->d_apps, sizeof(apps), cudaMemcpyDeviceToHost));
+  out8[2] = (double)(apps[OP_SLOT] + apps[OP_SHARED] + apps[OP_GENERIC] + apps[OP_IMPLICIT]);
+  out8[7] = (double)apps[OP_HYBRID];
+  if (reset) {
+    CK(cudaMemset(c->d_apps, 0, sizeof(apps)));
+    CK(cudaDeviceSynchronize());
+  }
   if (reset)
-    for (int i = 0; i < 6; ++i) c->prof_acc[i] = 0;
+    for (int i = 0; i < 8; ++i) c->prof_acc[i] = 0;
 }
 void mgpu_timer_start(mgpu_ctx *c) { CK(cudaEventRecord(c->t0, c->stream)); }
 float mgpu_timer_stop(mgpu_ctx *c) {

@@ -180,7 +180,9 @@ micropp<3>::micropp(const micropp_params_t &params)
     const double vals[8] = {m.E, m.nu, m.Ka, m.Sy, m.k, m.mu, m.lambda, m.Xt};
     memcpy(cfg.mat[i], vals, sizeof(vals));
     cfg.mat_type[i] = m.type;
-    if (m.type == MATERIAL_ELASTIC) elastic_element_matrix(bmat, m, wg, &ke[i * 576]);
+    // element matrix of the material's ELASTIC law: what an elastic material always has, and what a damage / plastic
+    // element has below its threshold (src/material.cpp:111-164, 206-287: the linear branch is lambda, mu elasticity)
+    elastic_element_matrix(bmat, m, wg, &ke[i * 576]);
   }
   cfg.ke_elastic = ke.data();
   cfg.nr_max_its = nr_max_its;
@@ -199,6 +201,7 @@ micropp<3>::micropp(const micropp_params_t &params)
   engine->ctx = mgpu_create(&cfg);
   engine->W = mgpu_wave_size(engine->ctx);
   engine->implicit = mgpu_implicit(engine->ctx) != 0;
+  engine->hybrid = mgpu_hybrid_available(engine->ctx) != 0;
   engine->use_A0 = use_A0;
   engine->its_with_A0 = its_with_A0;
   if (const char *env = getenv("MICROPP_CG_CHUNK")) engine->cg_chunk = std::max(1, atoi(env));
@@ -1012,8 +1015,11 @@ void micropp3x_prof_enable(micropp3 *s, int on) {
   mpp_access::engine((micropp<3> *)s->ptr)->profiling = on != 0;  // per-kernel events need plain stream launches
   mgpu_prof_enable(mpp_access::engine((micropp<3> *)s->ptr)->ctx, on);
 }
-void micropp3x_prof_read(micropp3 *s, double *out6, int reset) {
-  mgpu_prof_read(mpp_access::engine((micropp<3> *)s->ptr)->ctx, out6, reset);
+int micropp3x_hybrid_available(const micropp3 *s) {
+  return mgpu_hybrid_available(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
+}
+void micropp3x_prof_read(micropp3 *s, double *out8, int reset) {
+  mgpu_prof_read(mpp_access::engine((micropp<3> *)s->ptr)->ctx, out8, reset);
 }
 double micropp3x_last_homogenize_ms(const micropp3 *s) { return mpp_access::last_ms((micropp<3> *)s->ptr); }
 unsigned long long micropp3x_launch_count(const micropp3 *s) {
@@ -1104,7 +1110,9 @@ extern "C" mgpu_ctx *micropp3x_slab_create(const micropp3_params *q, int z0, int
     const double vals[8] = {m.E, m.nu, m.Ka, m.Sy, m.k, m.mu, m.lambda, m.Xt};
     memcpy(cfg.mat[i], vals, sizeof(vals));
     cfg.mat_type[i] = m.type;
-    if (m.type == MATERIAL_ELASTIC) elastic_element_matrix(bmat, m, wg, &ke[i * 576]);
+    // element matrix of the material's ELASTIC law: what an elastic material always has, and what a damage / plastic
+    // element has below its threshold (src/material.cpp:111-164, 206-287: the linear branch is lambda, mu elasticity)
+    elastic_element_matrix(bmat, m, wg, &ke[i * 576]);
   }
   cfg.ke_elastic = ke.data();
   cfg.nr_max_its = q->nr_max_its;

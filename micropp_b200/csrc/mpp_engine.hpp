@@ -15,13 +15,14 @@ struct mpp_engine {
   int its_with_A0 = 1;
   bool A0_ready = false;
   bool implicit = false;  // all-elastic RVE: DPCG on the implicit operator (mgpu_implicit), no Jacobian assembly
+  bool hybrid = false;    // damage / plastic phase: slots mostly inside their linear regime take the hybrid operator
   int cg_chunk = 8;
   int cg_group = 0;       // slots per L2-resident group of a Newton/DPCG solve (0: the whole wave at once)
   bool use_graphs = true;  // one CUDA graph per Newton step (MICROPP_GRAPHS=0: plain stream launches)
   bool profiling = false;  // per-kernel CUDA-event timing needs plain launches
 
   // device slot lists: 0 = caller's list, 1 = Newton-active, 2/4 = CG-active (ping-pong), 3 = caller's subset
-  enum { L_OUTER = 0, L_NEWTON = 1, L_CG_A = 2, L_SUB = 3, L_CG_B = 4 };
+  enum { L_OUTER = 0, L_NEWTON = 1, L_CG_A = 2, L_SUB = 3, L_CG_B = 4, L_HYB = 6 };
 
   // DPCG on the slots of `list` (src/ell.cpp:66-122).  The loop condition is evaluated on the device
   // per slot; the host only learns how many slots are still iterating, every cg_chunk iterations.
@@ -75,6 +76,31 @@ struct mpp_engine {
       // matrix assembly_mat would build, for every slot and every step (which also covers the A0 shortcut)
       auto op_of = [&](int step) { return implicit ? 3 : ((use_A0 && A0_ready && step <= its_with_A0 - 1) ? 1 : 0); };
       const int shared = op_of(it);
+      if (hybrid && shared == 0) {
+        // one Newton step at a time: every step re-probes which elements have left their linear regime, builds the
+        // node lists and sends every slot to the hybrid or to the fully assembled operator
+        int nh = 0, nf = 0;
+        mgpu_hybrid_split(ctx, L_NEWTON, na, &nh, &nf);
+        if (use_graphs && !profiling) {
+          mgpu_newton_step_graph_on(ctx, 1, nh, 4);
+          mgpu_newton_step_graph_on(ctx, 0, nf, 0);
+        } else {
+          if (nh > 0) {
+            mgpu_asm_mat_hyb(ctx, L_HYB, nh);
+            cg_solve(L_HYB, nh, 4);
+            mgpu_axpy_u(ctx, L_HYB, nh);
+            mgpu_asm_rhs(ctx, L_HYB, nh, 1);
+          }
+          if (nf > 0) {
+            mgpu_asm_mat(ctx, L_NEWTON, nf, 0);
+            cg_solve(L_NEWTON, nf, 0);
+            mgpu_axpy_u(ctx, L_NEWTON, nf);
+            mgpu_asm_rhs(ctx, L_NEWTON, nf, 1);
+          }
+        }
+        ++it;
+        continue;
+      }
       if (use_graphs && !profiling) {
         int left = na;
         while (left > 0) {  // every graph launch is one Newton step of all still-active slots

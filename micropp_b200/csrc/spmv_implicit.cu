@@ -704,13 +704,18 @@ void mgpu_int::launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
     // p.Ap: one warp per slot folds the per-(tile, warp) and per-block partials in a fixed order + the scalar tail
     // (fused slab path: k_slab_reduce_tail does the fold together with the cross-rank sum)
     c->last_spmv_nfold = t2.ntiles * t2.cb + nfb;
-    if (!c->slab_fused || force) {
+    if ((!c->slab_fused && !c->defer_fold) || force) {
       k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->last_spmv_nfold, force);
       c->launches++;
     }
   } else {
     k_spmv_dot_imp<MR><<<int_grid(c, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, force);
   }
+}
+
+// the p.Ap fold on its own (hybrid operator: after k_spmv_hyb has added its correction partials)
+void mgpu_int::launch_fold_spmv(mgpu_ctx *c, int l, int n, int nfold, int force) {
+  k_fold_spmv<<<dim3(1, n), 32, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, nfold, force);
 }
 
 extern "C" {
