@@ -201,8 +201,8 @@ void mgpu_ell_cols(int nx, int ny, int nz, int *cols /* [3nn][81] */, int device
 void mgpu_prof_enable(mgpu_ctx *, int on);
 /* accumulated since last reset: [0]=spmv ms, [1]=spmv launches, [2]=spmv slot-applications, [3]=asm_mat ms,
    [4]=asm_rhs ms, [5]=cg_update+pupdate ms, [6]=hybrid-operator spmv ms, [7]=its slot-applications ([0]..[2] then count
-   the other operators only) */
-void mgpu_prof_read(mgpu_ctx *, double *out8, int reset);
+   the other operators only), [8]=explicit rows streamed by those applications (sum of the listed-row counts) */
+void mgpu_prof_read(mgpu_ctx *, double *out9, int reset);
 void mgpu_timer_start(mgpu_ctx *);
 float mgpu_timer_stop(mgpu_ctx *); /* ms on the context stream (syncs) */
 /* isolated SpMV micro-benchmark on the first n slots of the pool (matrix contents as they are) */

@@ -112,7 +112,7 @@ int micropp3x_slab_operator(const struct micropp3x_slab *);
 
 /* measurement (CUDA events on the library's own stream) */
 void micropp3x_prof_enable(struct micropp3 *self, int on);
-void micropp3x_prof_read(struct micropp3 *self, double *out8, int reset);
+void micropp3x_prof_read(struct micropp3 *self, double *out9, int reset);
 int micropp3x_hybrid_available(const struct micropp3 *self); /* hybrid operator for RVEs with a damage / plastic phase */
 double micropp3x_last_homogenize_ms(const struct micropp3 *self);
 unsigned long long micropp3x_launch_count(const struct micropp3 *self);

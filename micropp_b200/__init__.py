@@ -359,10 +359,11 @@ class Micropp3:
         self.lib.micropp3x_prof_enable(C.byref(self.h), int(bool(on)))
 
     def prof_read(self, reset=True):
-        out = np.zeros(8)
+        out = np.zeros(9)
         self.lib.micropp3x_prof_read(C.byref(self.h), _d(out), int(bool(reset)))
         return dict(spmv_ms=out[0], spmv_launches=int(out[1]), spmv_slot_apps=int(out[2]), asm_mat_ms=out[3],
-                    asm_rhs_ms=out[4], cg_vec_ms=out[5], hybrid_spmv_ms=out[6], hybrid_slot_apps=int(out[7]))
+                    asm_rhs_ms=out[4], cg_vec_ms=out[5], hybrid_spmv_ms=out[6], hybrid_slot_apps=int(out[7]),
+                    hybrid_row_apps=int(out[8]))
 
     def hybrid_available(self):
         """True when RVEs with a damage / plastic phase may take the hybrid operator (implicit elastic row blocks +

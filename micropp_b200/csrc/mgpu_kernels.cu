@@ -1000,7 +1000,8 @@ __global__ void __launch_bounds__(NT)
 
 // u += du (src/solve.cpp:73) and newton.solver_its += cg_its (src/solve.cpp:71)
 __global__ void __launch_bounds__(NT)
-    k_axpy_u(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, unsigned long long *apps) {
+    k_axpy_u(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, unsigned long long *apps,
+             int op) {
   const int slot = slot_of(L);
   if (slot < 0) return;
   mgpu_slot_state *st = &T.state[slot];
@@ -1009,7 +1010,9 @@ __global__ void __launch_bounds__(NT)
   const int n = blockIdx.x * NT + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->solver_its += st->cg_its;
-    atomicAdd(apps, (unsigned long long)st->cg_its);  // operator applications of this solve (measurement)
+    atomicAdd(apps + (op & 7), (unsigned long long)st->cg_its);  // operator applications of this solve (measurement)
+    if (op == OP_HYBRID)  // explicit rows those applications streamed
+      atomicAdd(apps + 7, (unsigned long long)st->cg_its * (unsigned long long)T.hcnt[slot]);
   }
   if (n >= P.nn) return;
 #pragma unroll
@@ -2083,7 +2086,7 @@ void mgpu_cg_finish(mgpu_ctx *c, int l, int n) {
 void mgpu_axpy_u(mgpu_ctx *c, int l, int n) {
   if (n <= 0) return;
   ProfScope ps(c, 9, n);
-  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, c->d_apps + (c->cg_op & 7));
+  k_axpy_u<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, c->d_apps, c->cg_op);
   CK(cudaGetLastError());
 }
 void mgpu_ave_stress(mgpu_ctx *c, int l, int n) {
@@ -2573,7 +2576,8 @@ void mgpu_prof_enable(mgpu_ctx *c, int on) {
   prof_drain(c);
   c->prof = on != 0;
 }
-void mgpu_prof_read(mgpu_ctx *c, double *out8, int reset) {
+void mgpu_prof_read(mgpu_ctx *c, double *out9, int reset) {
+  double *out8 = out9;
   prof_drain(c);
   for (int i = 0; i < 8; ++i) out8[i] = c->prof_acc[i];
   // RVE applications of the operators, counted on the device (the DPCG iterations every slot really did)
@@ -2582,6 +2586,7 @@ void mgpu_prof_read(mgpu_ctx *c, double *out8, int reset) {
   CK(cudaMemcpy(apps, c->d_apps, sizeof(apps), cudaMemcpyDeviceToHost));
   out8[2] = (double)(apps[OP_SLOT] + apps[OP_SHARED] + apps[OP_GENERIC] + apps[OP_IMPLICIT]);
   out8[7] = (double)apps[OP_HYBRID];
+  out9[8] = (double)apps[7];  // sum over hybrid applications of the explicit rows each one streamed
   if (reset) {
     CK(cudaMemset(c->d_apps, 0, sizeof(apps)));
     CK(cudaDeviceSynchronize());

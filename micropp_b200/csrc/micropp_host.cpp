@@ -1018,8 +1018,8 @@ void micropp3x_prof_enable(micropp3 *s, int on) {
 int micropp3x_hybrid_available(const micropp3 *s) {
   return mgpu_hybrid_available(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
 }
-void micropp3x_prof_read(micropp3 *s, double *out8, int reset) {
-  mgpu_prof_read(mpp_access::engine((micropp<3> *)s->ptr)->ctx, out8, reset);
+void micropp3x_prof_read(micropp3 *s, double *out9, int reset) {
+  mgpu_prof_read(mpp_access::engine((micropp<3> *)s->ptr)->ctx, out9, reset);
 }
 double micropp3x_last_homogenize_ms(const micropp3 *s) { return mpp_access::last_ms((micropp<3> *)s->ptr); }
 unsigned long long micropp3x_launch_count(const micropp3 *s) {
