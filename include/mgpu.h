@@ -46,6 +46,8 @@ typedef struct mgpu_slot_state {
   int cg_its, cg_active;
   int nl_flag;                  /* OR of material->evolute() (src/update.cpp:49) */
   unsigned ticket;              /* last-block-done counter */
+  double *cg_hist;              /* device, [cg_hist_k]: |z| at the head of DPCG iteration i of the LAST solve (NULL = off) */
+  int cg_hist_k, pad_;
 } mgpu_slot_state;
 
 typedef struct mgpu_config {
@@ -198,6 +200,11 @@ void mgpu_stage_put_mat(mgpu_ctx *, int slot, const double *vals_ref_layout);
 void mgpu_ell_cols(int nx, int ny, int nz, int *cols /* [3nn][81] */, int device); /* regenerates src/ell-common.cpp:34-139 on the GPU */
 
 /* ---- measurement ---- */
+/* Residual history of the DPCG solves (test instrument): from now on every slot records |z| = sqrt(z.z) -- the quantity
+   src/ell.cpp:93-94 tests at the loop head -- of the first k iterations of its latest solve.  read: copies min(k, its+1)
+   values of `slot`, returns how many. */
+void mgpu_cg_history(mgpu_ctx *, int k);
+int mgpu_cg_history_read(mgpu_ctx *, int slot, double *out, int k);
 void mgpu_prof_enable(mgpu_ctx *, int on);
 /* accumulated since last reset: [0]=spmv ms, [1]=spmv launches, [2]=spmv slot-applications, [3]=asm_mat ms,
    [4]=asm_rhs ms, [5]=cg_update+pupdate ms, [6]=hybrid-operator spmv ms, [7]=its slot-applications ([0]..[2] then count

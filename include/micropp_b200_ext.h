@@ -109,10 +109,17 @@ void micropp3x_slab_planes(const struct micropp3x_slab *, int *z0, int *z1); /* 
 void micropp3x_slab_get_u(struct micropp3x_slab *, double *u_local /* [nzl*ny*nx][3] */);
 unsigned long long micropp3x_slab_launch_count(const struct micropp3x_slab *);
 int micropp3x_slab_operator(const struct micropp3x_slab *);
+/* test instrument: |z| at the head of the first k DPCG iterations of the latest solve (every slab holds the same
+   globally summed values); see mgpu_cg_history in mgpu.h */
+void micropp3x_slab_cg_history(struct micropp3x_slab *, int k);
+int micropp3x_slab_cg_history_read(struct micropp3x_slab *, double *out, int k);
 
 /* measurement (CUDA events on the library's own stream) */
 void micropp3x_prof_enable(struct micropp3 *self, int on);
 void micropp3x_prof_read(struct micropp3 *self, double *out9, int reset);
+void micropp3x_cg_history(struct micropp3 *self, int k);   /* test instrument, see mgpu_cg_history (slot = GP index
+                                                              inside the last wave) */
+int micropp3x_cg_history_read(struct micropp3 *self, int slot, double *out, int k);
 int micropp3x_hybrid_available(const struct micropp3 *self); /* hybrid operator for RVEs with a damage / plastic phase */
 double micropp3x_last_homogenize_ms(const struct micropp3 *self);
 unsigned long long micropp3x_launch_count(const struct micropp3 *self);

@@ -120,6 +120,7 @@ def load():
         "micropp3x_elem_colour": (C.c_int, [C.c_int] * 3),
         "micropp3x_prof_enable": (None, [H, C.c_int]),
         "micropp3x_prof_read": (None, [H, _dp, C.c_int]), "micropp3x_hybrid_available": (C.c_int, [H]),
+        "micropp3x_cg_history": (None, [H, C.c_int]), "micropp3x_cg_history_read": (C.c_int, [H, C.c_int, _dp, C.c_int]),
         "micropp3x_last_homogenize_ms": (C.c_double, [H]),
         "micropp3x_launch_count": (C.c_ulonglong, [H]),
         "micropp3x_bench_spmv": (C.c_double, [H, C.c_int, C.c_int]),
@@ -364,6 +365,15 @@ class Micropp3:
         return dict(spmv_ms=out[0], spmv_launches=int(out[1]), spmv_slot_apps=int(out[2]), asm_mat_ms=out[3],
                     asm_rhs_ms=out[4], cg_vec_ms=out[5], hybrid_spmv_ms=out[6], hybrid_slot_apps=int(out[7]),
                     hybrid_row_apps=int(out[8]))
+
+    def cg_history(self, k):
+        """Test instrument: record |z| at the head of the first k DPCG iterations of every slot's latest solve."""
+        self.lib.micropp3x_cg_history(C.byref(self.h), int(k))
+
+    def cg_history_read(self, slot, k):
+        out = np.zeros(k)
+        n = self.lib.micropp3x_cg_history_read(C.byref(self.h), int(slot), _d(out), int(k))
+        return out[:n]
 
     def hybrid_available(self):
         """True when RVEs with a damage / plastic phase may take the hybrid operator (implicit elastic row blocks +

@@ -257,6 +257,7 @@ __device__ __forceinline__ void tail_cg_init(const MeshConst &P, mgpu_slot_state
   st->pnorm0 = pn;
   st->pnorm = pn;
   st->cg_its = 0;
+  if (st->cg_hist && st->cg_hist_k > 0) st->cg_hist[0] = pn;
   // loop head of src/ell.cpp:93-94
   st->cg_active = (0 < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < pn * P.cg_rel_tol);
 }
@@ -270,6 +271,7 @@ __device__ __forceinline__ void tail_cg_update(const MeshConst &P, mgpu_slot_sta
   st->beta = rz_n / st->rz;
   st->rz = rz_n;
   const int its = ++st->cg_its;
+  if (st->cg_hist && its < st->cg_hist_k) st->cg_hist[its] = pn;
   st->cg_active = (its < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < st->pnorm0 * P.cg_rel_tol);
 }
 
@@ -422,6 +424,8 @@ struct mgpu_ctx {
   mgpu_int::SlotTables T{};
   int *d_list[mgpu_int::NLIST] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int *d_count = nullptr;
+  double *d_cg_hist = nullptr;           // [W][cg_hist_k] (mgpu_cg_history)
+  int cg_hist_k = 0;
   unsigned long long *d_apps = nullptr;  // [8] DPCG iterations done per operator (measurement)
   int *d_cnt2 = nullptr;           // device-side list lengths used inside graphs: [0] Newton list, [1] CG list
   const int *dyn_count = nullptr;  // non-null while a graph is being captured: launches test it per block

@@ -1796,6 +1796,7 @@ void mgpu_destroy(mgpu_ctx *c) {
   cudaFreeHost(c->h_count);
   cudaFree(c->d_cnt2);
   cudaFree(c->d_apps);
+  if (c->d_cg_hist) cudaFree(c->d_cg_hist);
   for (auto &kv : c->step_graphs) cudaGraphExecDestroy(kv.second.exec);
   cudaFree(c->d_elem_type);
   cudaFree(c->d_ke);
@@ -2572,6 +2573,31 @@ void mgpu_apply_operator(mgpu_ctx *c, int l, int n, int op, int imp_kernel) {
 }
 
 // ---- measurement ---------------------------------------------------------------------------------
+void mgpu_cg_history(mgpu_ctx *c, int k) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_cg_hist) CK(cudaFree(c->d_cg_hist));
+  c->d_cg_hist = nullptr;
+  c->cg_hist_k = k > 0 ? k : 0;
+  if (k > 0) {
+    CK(cudaMalloc(&c->d_cg_hist, sizeof(double) * (size_t)k * c->W));
+    CK(cudaMemset(c->d_cg_hist, 0, sizeof(double) * (size_t)k * c->W));
+  }
+  // the pointer lives in the slot state (device memory read at run time), so captured graphs need no rebuild
+  for (int s = 0; s < c->W; ++s) {
+    double *ptr = k > 0 ? c->d_cg_hist + (size_t)s * k : nullptr;
+    CK(cudaMemcpy(&c->T.state[s].cg_hist, &ptr, sizeof(ptr), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&c->T.state[s].cg_hist_k, &c->cg_hist_k, sizeof(int), cudaMemcpyHostToDevice));
+  }
+}
+int mgpu_cg_history_read(mgpu_ctx *c, int slot, double *out, int k) {
+  if (!c->d_cg_hist || slot < 0 || slot >= c->W) return 0;
+  CK(cudaStreamSynchronize(c->stream));
+  mgpu_slot_state st;
+  CK(cudaMemcpy(&st, c->T.state + slot, sizeof(st), cudaMemcpyDeviceToHost));
+  const int n = std::min(std::min(k, c->cg_hist_k), st.cg_its + 1);
+  if (n > 0) CK(cudaMemcpy(out, c->d_cg_hist + (size_t)slot * c->cg_hist_k, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return n;
+}
 void mgpu_prof_enable(mgpu_ctx *c, int on) {
   prof_drain(c);
   c->prof = on != 0;

@@ -1015,6 +1015,10 @@ void micropp3x_prof_enable(micropp3 *s, int on) {
   mpp_access::engine((micropp<3> *)s->ptr)->profiling = on != 0;  // per-kernel events need plain stream launches
   mgpu_prof_enable(mpp_access::engine((micropp<3> *)s->ptr)->ctx, on);
 }
+void micropp3x_cg_history(micropp3 *s, int k) { mgpu_cg_history(mpp_access::engine((micropp<3> *)s->ptr)->ctx, k); }
+int micropp3x_cg_history_read(micropp3 *s, int slot, double *out, int k) {
+  return mgpu_cg_history_read(mpp_access::engine((micropp<3> *)s->ptr)->ctx, slot, out, k);
+}
 int micropp3x_hybrid_available(const micropp3 *s) {
   return mgpu_hybrid_available(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
 }

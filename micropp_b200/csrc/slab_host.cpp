@@ -219,4 +219,6 @@ void micropp3x_slab_planes(const micropp3x_slab *s, int *z0, int *z1) {
 void micropp3x_slab_get_u(micropp3x_slab *s, double *u_local) { mgpu_stage_get_u(s->ctx, kSlot, u_local); }
 unsigned long long micropp3x_slab_launch_count(const micropp3x_slab *s) { return mgpu_launch_count(s->ctx); }
 int micropp3x_slab_operator(const micropp3x_slab *s) { return s->op; }
+void micropp3x_slab_cg_history(micropp3x_slab *s, int k) { mgpu_cg_history(s->ctx, k); }
+int micropp3x_slab_cg_history_read(micropp3x_slab *s, double *out, int k) { return mgpu_cg_history_read(s->ctx, 0, out, k); }
 }

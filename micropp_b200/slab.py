@@ -337,6 +337,7 @@ def _bind_cxx(lib):
         "micropp3x_slab_homogenize_local": (C.c_int, [C.POINTER(V), C.c_int, _dp, _dp, _ip]),
         "micropp3x_slab_planes": (None, [V, _ip, _ip]), "micropp3x_slab_get_u": (None, [V, _dp]),
         "micropp3x_slab_launch_count": (C.c_ulonglong, [V]), "micropp3x_slab_operator": (C.c_int, [V]),
+        "micropp3x_slab_cg_history": (None, [V, C.c_int]), "micropp3x_slab_cg_history_read": (C.c_int, [V, _dp, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -429,6 +430,16 @@ class SlabRVECxx:
 
     def launch_count(self) -> int:
         return sum(int(self.lib.micropp3x_slab_launch_count(s)) for s in self.slabs)
+
+    def cg_history(self, k):
+        """Test instrument: record |z| at the head of the first k DPCG iterations of the latest solve."""
+        for s in self.slabs:
+            self.lib.micropp3x_slab_cg_history(s, int(k))
+
+    def cg_history_read(self, k, slab=0):
+        out = np.zeros(k)
+        n = self.lib.micropp3x_slab_cg_history_read(self.slabs[slab], out.ctypes.data_as(_dp), int(k))
+        return out[:n]
 
     def peer_error(self) -> int:
         return self._err

@@ -489,7 +489,14 @@ static double dot(const double *a, const double *b, int n) {
 }
 
 /* src/ell.cpp:66-122: Jacobi-preconditioned CG; the convergence test sits at the head of the loop */
+int orc_ell_solve_cgpd_hist(int nx, int ny, int nz, const double *vals, const double *b, double *x, double *err,
+                            double *hist, int nhist);
 int orc_ell_solve_cgpd(int nx, int ny, int nz, const double *vals, const double *b, double *x, double *err) {
+  return orc_ell_solve_cgpd_hist(nx, ny, nz, vals, b, x, err, NULL, 0);
+}
+/* the same solver; hist[i] = the |z| that the loop-head test of iteration i sees (i < nhist) */
+int orc_ell_solve_cgpd_hist(int nx, int ny, int nz, const double *vals, const double *b, double *x, double *err,
+                            double *hist, int nhist) {
   const int nn = nx * ny * nz, nrow = nn * 3;
   int *cols = (int *)malloc((size_t)nrow * NNZ * sizeof(int));
   double *w = (double *)malloc((size_t)nrow * 5 * sizeof(double));
@@ -513,6 +520,7 @@ int orc_ell_solve_cgpd(int nx, int ny, int nz, const double *vals, const double 
   double pnorm = pnorm0;
   int its = 0;
   while (its < CG_MAX_ITS) {
+    if (hist && its < nhist) hist[its] = pnorm;
     if (pnorm < CG_ABS_TOL || pnorm < pnorm0 * CG_REL_TOL) break;
     MVP(p, Ap);
     const double alpha = rz / dot(p, Ap, nrow);

@@ -129,6 +129,16 @@ def ell_solve_cgpd(nx, ny, nz, vals, b):
     return x, int(its), float(err.value)
 
 
+def ell_solve_cgpd_hist(nx, ny, nz, vals, b, k):
+    """ell_solve_cgpd + hist[i] = |z| seen by the loop-head test of iteration i (i < k)."""
+    x = np.zeros(3 * nx * ny * nz)
+    err = C.c_double(0.0)
+    hist = np.zeros(k)
+    its = load().orc_ell_solve_cgpd_hist(nx, ny, nz, _d(np.ascontiguousarray(vals)), _d(np.ascontiguousarray(b)), _d(x),
+                                         C.byref(err), _d(hist), int(k))
+    return x, int(its), hist[:min(k, int(its) + 1)]
+
+
 class OrcProblem:
     """One RVE mesh + materials (the FE stages of the reference's micropp<3>)."""
 

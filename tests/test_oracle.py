@@ -238,3 +238,18 @@ def test_full_size_fixture_inputs_are_the_bench_load_path(workload):
         assert np.array_equal(f["eps"][k], bench.strains_for(workload, wl["ngp"], 0, k)[gps])
     assert f["nl"][-1].all() and np.all(np.isfinite(f["sig"]))
     assert f["eps"].shape[0] == wl["prep_steps"] + 1          # the fixture covers the step bench.py times
+
+
+def test_cg_residual_history_is_the_plain_solver():
+    """orc_ell_solve_cgpd_hist is orc_ell_solve_cgpd (src/ell.cpp:66-122) + a record of the |z| its loop-head test sees:
+    same iterate, same count; hist[0] = |z_0|, the last recorded value is the first one under the tolerance."""
+    p = O.OrcProblem(dict(size=(6, 5, 7), lin_stress=False, **CASES["elastic_sphere"]))
+    u = p.set_displ_bc(np.array([1e-3, -2e-4, 3e-4, 5e-4, 0.0, -1e-4]))
+    b, _ = p.assembly_rhs(u)
+    vals = p.assembly_mat(u)
+    x0, its0, _ = O.ell_solve_cgpd(6, 5, 7, vals, b)
+    x1, its1, hist = O.ell_solve_cgpd_hist(6, 5, 7, vals, b, 1000)
+    assert its0 == its1 and np.array_equal(x0, x1) and len(hist) == its1 + 1
+    assert np.all(hist[:-1] >= hist[0] * 1e-5) and hist[-1] < hist[0] * 1e-5
+    _, _, short = O.ell_solve_cgpd_hist(6, 5, 7, vals, b, 4)
+    assert np.array_equal(short, hist[:4])
