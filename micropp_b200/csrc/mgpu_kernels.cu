@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT)
 // ------------------------------------------------------------------------------------------------
 // assembly_mat, general (damage / plastic / mixed), in two kernels.
 //
-// (1) k_elem_ctan: thread per element.  Gathers the 24 element dofs once and evaluates the reference's
+// (1) k_elem_ctan: thread per (element, Gauss point).  Gathers the 24 element dofs and evaluates the reference's
 //     forward-difference tangent (src/material.cpp:49-63: 7 stress evaluations) at the 8 Gauss points,
 //     storing C_gp (36 doubles, row-major) into a scratch buffer laid out [(gp*36+q)][nelem_pad] per
 //     slot of the current chunk, so stores and the later loads are coalesced over elements.  Every
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NT)
 constexpr int GN = 16;      // nodes per block of the gather kernel (GN*8 == NT)
 constexpr int CTAN_LEN = 8 * 36;  // doubles per element in the tangent scratch
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
     k_elem_ctan(const __grid_constant__ MeshConst P, const Lst L, SlotTables T,
                 const double *__restrict__ u_pool, size_t vstride, const int *__restrict__ elem_type,
                 double *__restrict__ cbuf, size_t cstride, int hybrid) {
@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(NT)
   const double *u = u_pool + (size_t)slot * vstride;
   const double *vars = T.vars_old[slot];
   double *cb = cbuf + (size_t)blockIdx.y * cstride;
-  const int e = blockIdx.x * NT + threadIdx.x;
+  // thread per (element, Gauss point); the Gauss point is uniform over a block (grid.x = 8 * blocks per element sweep)
+  const int nblk_e = (P.nelem + NT - 1) / NT;
+  const int gp = blockIdx.x / nblk_e;
+  const int e = (blockIdx.x - gp * nblk_e) * NT + threadIdx.x;
   if (e >= P.nelem) return;
   const int type = __ldg(&elem_type[e]);
   const mpp_material m = P.mat[type];
@@ -329,15 +332,12 @@ __global__ void __launch_bounds__(NT)
   double ue[24];
   gather_ue(P, u, ex, ey, ez, ue);
   const int nv = mat_nvar(m.type);
-#pragma unroll 1
-  for (int gp = 0; gp < 8; ++gp) {
-    double eps[6], C[36], vbuf[7];
-    gp_strain(P.dsh[gp], ue, eps);
-    const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
-    mat_ctan(m, eps, v, C);
+  double eps[6], C[36], vbuf[7];
+  gp_strain(P.dsh[gp], ue, eps);
+  const double *v = fetch_vars(vars, P.nelem_pad, e, gp, nv, vbuf);
+  mat_ctan(m, eps, v, C);
 #pragma unroll
-    for (int q = 0; q < 36; ++q) cb[(size_t)(gp * 36 + q) * P.nelem_pad + e] = C[q];
-  }
+  for (int q = 0; q < 36; ++q) cb[(size_t)(gp * 36 + q) * P.nelem_pad + e] = C[q];
 }
 
 __global__ void __launch_bounds__(NT)
@@ -1996,8 +1996,9 @@ static void asm_mat_impl(mgpu_ctx *c, int l, int n, int to_shared, int hybrid) {
     for (int off = 0; off < n; off += c->ctan_chunk) {
       const int cnt = std::min(c->ctan_chunk, n - off);
       const Lst lst = lst_of(c, l, off);
-      k_elem_ctan<<<elem_grid(c, cnt), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
-                                                          c->d_ctan, cstride, hybrid);
+      const dim3 ge = elem_grid(c, cnt);
+      k_elem_ctan<<<dim3(8 * ge.x, ge.y), NT, 0, c->stream>>>(c->mc, lst, c->T, c->V.u, c->V.vstride, c->d_elem_type,
+                                                             c->d_ctan, cstride, hybrid);
       dim3 g(std::max((c->mc.nint + GN - 1) / GN, 1), cnt);
       k_asm_mat_general<<<g, NT, GN * NPLANE * sizeof(double), c->stream>>>(
           c->mc, lst, c->V.mat, c->V.mstride, shared, c->d_elem_type, c->d_ke, c->d_ctan, cstride, c->T, hybrid);
