@@ -697,8 +697,14 @@ void mgpu_int::launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern) {
                                                                     rs, force);
     const int nfb = (c->nfix + NT - 1) / NT;
     if (nfb > 0) {  // the nodes no chunk keeps (stream order: after the zeros the tile stores put there)
-      k_spmv_fix<MR><<<dim3(nfb, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, c->d_fixn,
-                                                                        c->nfix, t2.ntiles * t2.cb, force);
+      // few interface nodes x few slots: 2 slots per thread instead of 8, so that the grid still covers the SMs (the
+      // kernel is a latency chain of 243 gathers per slot; the sums of a slot do not depend on the grouping)
+      if ((long)nfb * ((n + MR - 1) / MR) < 148L * 3)
+        k_spmv_fix<2><<<dim3(nfb, (n + 1) / 2), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, c->d_fixn,
+                                                                    c->nfix, t2.ntiles * t2.cb, force);
+      else
+        k_spmv_fix<MR><<<dim3(nfb, (n + MR - 1) / MR), NT, 0, c->stream>>>(c->mc, lst_of(c, l), n, c->T, c->V, c->d_fixn,
+                                                                          c->nfix, t2.ntiles * t2.cb, force);
       c->launches++;
     }
     // p.Ap: one warp per slot folds the per-(tile, warp) and per-block partials in a fixed order + the scalar tail
