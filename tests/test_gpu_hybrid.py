@@ -133,3 +133,54 @@ def test_hybrid_fe_full_tangent_and_mixed_coupling(mpp, refpy):
         print(f"hybrid FE_FULL ctan {case}: worst relative difference to the reference {worst:.3e}")
         assert worst < 1e-8, (case, worst)
         g.close()
+
+
+def test_hybrid_subiterations_with_default_linear_shortcuts(mpp, refpy):
+    """Sub-iterations (src/homogenize.cpp:137-166: the strain increment applied in nsubiterations pieces when Newton
+    fails) with a small Newton budget and the constructor's defaults (lin_stress, calc_ctan_lin = true) -- the hybrid
+    operator is chosen anew in every Newton solve of every sub-step."""
+    ngp, n = 3, 8
+    kw = dict(ngp=ngp, coupling=[mpp.FE_ONE_WAY] * ngp, nr_max_its=2, subiterations=True, nsubiterations=3)
+    path = _path("damage_sphere", ngp, 8, 0)
+    g = mpp.Micropp3(mk(mpp, "damage_sphere", n, **kw))
+    r = refpy.RefMicropp(mk(refpy, "damage_sphere", n, **kw))
+    assert g.hybrid_available()
+    hg, pr = _run_prof(g, path)
+    hr = run_history(r, path)
+    assert pr["hybrid_slot_apps"] > 0 and any(any(h["sub"]) for h in hr)   # sub-iterations really happened
+    compare_histories(hg, hr, newton_budget=40)
+
+
+def test_hybrid_multi_wave_and_restart(mpp, monkeypatch, tmp_path):
+    """Waves smaller than ngp (FE state parked between waves) and a restart file in the middle of the load path: both
+    must continue bit-identically -- the lists of the hybrid operator are derived state, rebuilt from u and the internal
+    variables at every Newton iteration."""
+    monkeypatch.chdir(tmp_path)
+    ngp, n, case = 5, 8, "damage_sphere"
+    kw = dict(ngp=ngp, lin_stress=False, calc_ctan_lin=False, nr_max_its=12)
+    path = _path(case, ngp, 8, 0)
+    monkeypatch.setenv("MICROPP_WAVE", "2")
+    a = mpp.Micropp3(mk(mpp, case, n, **kw))
+    assert a.wave_size() == 2
+    monkeypatch.delenv("MICROPP_WAVE")
+    b = mpp.Micropp3(mk(mpp, case, n, **kw))
+    ha, hb = run_history(a, path[:5]), run_history(b, path[:5])
+    assert any(hb[-1]["nl"])
+    b.write_restart(3)
+    c = mpp.Micropp3(mk(mpp, case, n, **kw))
+    c.read_restart(3)
+    ha += run_history(a, path[5:])
+    hb += run_history(b, path[5:])
+    hc = run_history(c, path[5:])
+    for x, y in zip(ha, hb):
+        assert np.array_equal(x["sig"], y["sig"])
+        assert x["cost"] == y["cost"] and x["nl"] == y["nl"] and x["conv"] == y["conv"]
+    for x, y in zip(hc, hb[5:]):
+        # Gauss points that were still linear when the file was written restart from u = 0 instead of their
+        # converged u_n (the reference's format stores u only with the internal variables): same solution, other path
+        for gp in range(ngp):
+            if hb[4]["nl"][gp]:
+                assert np.array_equal(x["sig"][gp], y["sig"][gp]) and x["cost"][gp] == y["cost"][gp]
+            else:
+                assert relerr(x["sig"][gp], y["sig"][gp]) < 1e-4      # two DPCG solves to a 1e-5 reduction
+        assert x["nl"] == y["nl"]
