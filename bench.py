@@ -594,7 +594,7 @@ def run_slab(M, env: Env, n: int, reps: int):
 
 # ------------------------------------------------------------------------------------------------ main
 METRIC = "homogenized GPs/sec (DPCG+assembly)"
-EXTRA_NGP = {"damage50": 64, "plastic40": 64, "elastic30": 1024}
+EXTRA_NGP = {"damage50": 128, "plastic40": 128, "elastic30": 1024}
 
 
 def main():

@@ -185,6 +185,7 @@ void *mgpu_stream(mgpu_ctx *);   /* the cudaStream_t every launch of this contex
 
 /* ---- results ---- */
 void mgpu_fetch_state(mgpu_ctx *, int n, const int *slots, mgpu_slot_state *out); /* syncs */
+int mgpu_slot_state_size(void); /* sizeof(mgpu_slot_state): bindings that mirror the struct check it when they load */
 void mgpu_fetch_stress(mgpu_ctx *, int n, const int *slots, double *sig6);        /* syncs */
 void mgpu_clear_nl_flags(mgpu_ctx *, int which_list, int n);
 

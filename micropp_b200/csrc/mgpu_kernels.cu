@@ -26,6 +26,10 @@
 // The implicit-operator SpMV kernels live in spmv_implicit.cu; shared structures and helpers in mgpu_internal.cuh.
 #include "mgpu_internal.cuh"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 using namespace mgpu_int;
 
 namespace {
@@ -1533,7 +1537,22 @@ int mgpu_device_count(void) {
   return n;
 }
 
+// MICROPP_SEGV_TRACE=1: native backtrace on SIGSEGV / SIGABRT (debugging aid; off by default)
+static void segv_trace(int sig) {
+  void *bt[64];
+  const int n = backtrace(bt, 64);
+  const char msg[] = "micropp-b200: fatal signal, native backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
 mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
+  static bool trace_installed = false;
+  if (!trace_installed && getenv("MICROPP_SEGV_TRACE")) {
+    trace_installed = true;
+    signal(SIGSEGV, segv_trace);
+    signal(SIGABRT, segv_trace);
+  }
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0) {
@@ -1822,6 +1841,7 @@ void mgpu_sync(mgpu_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
 }
 unsigned long long mgpu_launch_count(const mgpu_ctx *c) { return c->launches; }
+int mgpu_slot_state_size(void) { return (int)sizeof(mgpu_slot_state); }
 
 // ---- per-GP persistent state ---------------------------------------------------------------
 void mgpu_gp_swap(mgpu_ctx *c, int gp) {

@@ -43,7 +43,8 @@ class SlotState(C.Structure):
     _fields_ = [("norm0", C.c_double), ("norm", C.c_double), ("rz", C.c_double), ("pAp", C.c_double),
                 ("alpha", C.c_double), ("beta", C.c_double), ("pnorm0", C.c_double), ("pnorm", C.c_double),
                 ("nr_its", C.c_int), ("solver_its", C.c_int), ("nr_active", C.c_int), ("converged", C.c_int),
-                ("cg_its", C.c_int), ("cg_active", C.c_int), ("nl_flag", C.c_int), ("ticket", C.c_uint)]
+                ("cg_its", C.c_int), ("cg_active", C.c_int), ("nl_flag", C.c_int), ("ticket", C.c_uint),
+                ("cg_hist", C.c_void_p), ("cg_hist_k", C.c_int), ("pad_", C.c_int)]
 
 
 def plane_range(nz: int, nslabs: int, s: int) -> tuple[int, int]:
@@ -100,6 +101,10 @@ def _bind(lib):
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args
+    lib.mgpu_slot_state_size.restype = C.c_int
+    if lib.mgpu_slot_state_size() != C.sizeof(SlotState):   # mgpu_fetch_state writes whole structs into our mirror
+        raise RuntimeError(f"slab.py: SlotState mirrors {C.sizeof(SlotState)} bytes, mgpu_slot_state has "
+                           f"{lib.mgpu_slot_state_size()} (include/mgpu.h changed)")
     lib._slab_bound = True
 
 

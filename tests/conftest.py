@@ -26,6 +26,15 @@ def pytest_collection_modifyitems(config, items):
     pass
 
 
+@pytest.fixture(autouse=True)
+def _finalize_after_each_test():
+    """Objects that own device memory (Micropp3, SlabRVE, the compiled reference) are finalized when THEIR test ends,
+    not at some later allocation of another test: a crash in a destructor is then reported against its own test."""
+    yield
+    import gc
+    gc.collect()
+
+
 @pytest.fixture(scope="session")
 def refpy():
     """The compiled reference (oracle/_ref) -- the checker."""

@@ -54,3 +54,15 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert "this library has no CPU path" in src
     pkg = "".join(p.read_text() for p in (ROOT / "micropp_b200").glob("*.py"))
     assert "oracle" not in pkg.replace("# oracle", ""), "the product package must never import the oracle"
+
+
+def test_ctypes_mirrors_match_the_c_structs():
+    """Every ctypes.Structure the bindings hand to the library as an OUTPUT buffer has the size the C side writes
+    (a 16-byte mismatch of SlotState once corrupted the heap of the test process)."""
+    import ctypes as C
+    import micropp_b200
+    from micropp_b200 import slab
+    lib = C.CDLL(str(micropp_b200.LIB_PATH))
+    lib.mgpu_slot_state_size.restype = C.c_int
+    assert lib.mgpu_slot_state_size() == C.sizeof(slab.SlotState)
+    assert C.sizeof(slab.SlabHandle) == 72          # struct micropp3x_slab_handle {char mail[64]; int op, pad;}
