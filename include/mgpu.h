@@ -131,6 +131,19 @@ void mgpu_cg_pupdate(mgpu_ctx *, int which_list, int n);
 /* x += alpha p of the last iteration (deferred from mgpu_cg_update to mgpu_cg_pupdate, which the last iteration
    of a slot skips): call once after the DPCG loop, before du is used */
 void mgpu_cg_finish(mgpu_ctx *, int which_list, int n);
+/* Cluster-resident DPCG (cg_resident.cu): the WHOLE solve of src/ell.cpp:66-122 -- cg_init, every iteration, the
+   deferred x update -- of each slot of the list in ONE launch, one thread-block cluster per RVE with p, du in shared
+   memory and r in registers.  Available (mgpu_resident != 0) for all-elastic RVEs that fit a cluster (30^3 does);
+   MICROPP_RESIDENT=0 keeps the three-kernel loop.  info: meta[8] = {CTAs per cluster, py, pz, nodes per thread,
+   threads per CTA, shared-memory bytes, interface entries of the busiest CTA, clusters in flight}. */
+int mgpu_resident(const mgpu_ctx *);
+void mgpu_resident_info(const mgpu_ctx *, int *meta8);
+void mgpu_cg_resident(mgpu_ctx *, int which_list, int n);
+double mgpu_prof_resident_ms(mgpu_ctx *, int reset);
+float mgpu_bench_resident(mgpu_ctx *, int n, int reps, int dbg); /* isolated timing, see cg_resident.cu */
+/* host-only replay of the plan of the cluster-resident kernel (CPU tests): see cg_resident.cu */
+int mgpu_resident_replay_host(int nx, int ny, int nz, const int *elem_type, const double *rows_pure, const double *ke,
+                              const double *p, double *Ap, int *meta8, int force_cs);
 void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);
 void mgpu_ave_stress(mgpu_ctx *, int which_list, int n);
 void mgpu_vars_new(mgpu_ctx *, int which_list, int n, int write);

@@ -54,6 +54,11 @@ int micropp3x_wave_size(const struct micropp3 *self);
 int micropp3x_implicit_rows(const struct micropp3 *self);
 /* -1: assembled matrices; else the implicit SpMV kernel in use: 0 k_spmv_dot_imp (odd nx), 3 k_spmv_dot_tmac */
 int micropp3x_implicit_kernel(const struct micropp3 *self);
+/* cluster-resident DPCG (whole solve in one launch, one thread-block cluster per RVE; see mgpu_cg_resident):
+   returns the CTAs per cluster (0 = the three-kernel loop runs) and fills meta8 as mgpu_resident_info (may be NULL) */
+int micropp3x_resident_info(const struct micropp3 *self, int *meta8);
+/* profiling mode: accumulated time of the cluster-resident DPCG solves */
+double micropp3x_prof_resident_ms(struct micropp3 *self, int reset);
 void micropp3x_get_elem_type(const struct micropp3 *self, int *out);
 void micropp3x_get_bmat(const struct micropp3 *self, double *out /* [8][6][24] */);
 void micropp3x_get_ctan_lin(const struct micropp3 *self, double *out36);
@@ -126,6 +131,8 @@ unsigned long long micropp3x_launch_count(const struct micropp3 *self);
 double micropp3x_bench_spmv(struct micropp3 *self, int nslots, int iters); /* ms per launch */
 /* implicit elastic operator; kern: -1 the context's kernel, 0 k_spmv_dot_imp, 3 k_spmv_dot_tmac + k_spmv_fix */
 double micropp3x_bench_imp_spmv(struct micropp3 *self, int nslots, int iters, int kern);
+/* isolated timing of the cluster-resident DPCG kernel (mgpu_bench_resident); ms per launch, -1 when unavailable */
+double micropp3x_bench_resident(struct micropp3 *self, int nslots, int reps, int dbg);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ def load():
         "micropp3x_nndim": (C.c_int, [H]),
         "micropp3x_wave_size": (C.c_int, [H]), "micropp3x_implicit_rows": (C.c_int, [H]),
         "micropp3x_implicit_kernel": (C.c_int, [H]),
+        "micropp3x_resident_info": (C.c_int, [H, _ip]), "micropp3x_prof_resident_ms": (C.c_double, [H, C.c_int]),
         "micropp3x_apply_operator": (C.c_double, [H, _dp, _dp, C.c_int, C.c_int]),
         "micropp3x_get_elem_type": (None, [H, _ip]),
         "micropp3x_get_bmat": (None, [H, _dp]),
@@ -125,6 +126,7 @@ def load():
         "micropp3x_launch_count": (C.c_ulonglong, [H]),
         "micropp3x_bench_spmv": (C.c_double, [H, C.c_int, C.c_int]),
         "micropp3x_bench_imp_spmv": (C.c_double, [H, C.c_int, C.c_int, C.c_int]),
+        "micropp3x_bench_resident": (C.c_double, [H, C.c_int, C.c_int, C.c_int]),
         "material_set": (None, [C.POINTER(MaterialBase), C.c_int] + [C.c_double] * 5),
         "mgpu_device_count": (C.c_int, []),
     }
@@ -298,6 +300,17 @@ class Micropp3:
     def implicit_rows(self):
         return int(self.lib.micropp3x_implicit_rows(C.byref(self.h)))
 
+    def resident_info(self):
+        """Cluster-resident DPCG (whole solve in one launch, one thread-block cluster per RVE): None when the
+        three-kernel loop runs, else dict(cs, py, pz, tn, threads, smem, fixcap, clusters)."""
+        meta = np.zeros(8, dtype=np.int32)
+        if int(self.lib.micropp3x_resident_info(C.byref(self.h), meta.ctypes.data_as(_ip))) == 0:
+            return None
+        return dict(zip(("cs", "py", "pz", "tn", "threads", "smem", "fixcap", "clusters"), (int(v) for v in meta)))
+
+    def prof_resident_ms(self, reset=True):
+        return float(self.lib.micropp3x_prof_resident_ms(C.byref(self.h), int(bool(reset))))
+
     def elem_type(self):
         out = np.zeros(max(self.nelem, 1), dtype=np.int32)
         self.lib.micropp3x_get_elem_type(C.byref(self.h), out.ctypes.data_as(_ip))
@@ -388,6 +401,10 @@ class Micropp3:
 
     def bench_spmv(self, nslots, iters=20):
         return float(self.lib.micropp3x_bench_spmv(C.byref(self.h), int(nslots), int(iters)))
+
+    def bench_resident(self, nslots, reps=3, dbg=4):
+        """ms per isolated launch of the cluster-resident DPCG kernel over nslots RVEs (dbg bit 4: exactly 60 iterations)."""
+        return float(self.lib.micropp3x_bench_resident(C.byref(self.h), int(nslots), int(reps), int(dbg)))
 
     def bench_imp_spmv(self, nslots, iters=20, kern=2):
         """ms per application of the implicit elastic operator on `nslots` RVEs (kern: 2 context default, 10+v TMA variant v)."""

@@ -16,7 +16,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmicropp_b200.so"
 
-SOURCES = ["mgpu_kernels.cu", "spmv_implicit.cu", "ell_generic.cu", "micropp_host.cpp", "micropp_geometry.cpp", "material_host.cpp", "ell_host.cpp", "slab_host.cpp",
+SOURCES = ["mgpu_kernels.cu", "spmv_implicit.cu", "cg_resident.cu", "ell_generic.cu", "micropp_host.cpp", "micropp_geometry.cpp", "material_host.cpp", "ell_host.cpp", "slab_host.cpp",
            "micropp_c.cpp"]
 HEADERS = list((ROOT / "include").glob("*.h*")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp"))
 

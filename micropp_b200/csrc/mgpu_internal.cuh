@@ -377,8 +377,14 @@ __host__ __device__ inline size_t slab_mail_bytes() { return (sizeof(SlabMail) +
 
 }  // namespace mgpu_int
 
+namespace mgpu_int {
+struct ResState;  // cg_resident.cu: plan + device tables of the cluster-resident DPCG
+}
+
 struct mgpu_ctx {
   // (types of namespace mgpu_int)
+  mgpu_int::ResState *res = nullptr;  // non-null: DPCG solves of the implicit operator run as ONE cluster-resident kernel
+  double prof_res_ms = 0;             // profiling: time of those solves
 
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -512,5 +518,10 @@ void launch_imp_spmv(mgpu_ctx *c, int l, int n, int force, int kern);
 void launch_fold_spmv(mgpu_ctx *c, int l, int n, int nfold, int force);
 void build_row_blocks(mgpu_ctx *c, const std::vector<int> &codes);  // mgpu_kernels.cu (k_rows_build)
 enum { IMP_SIMPLE = 0, IMP_TMAC = 3 };
+
+// ---- cluster-resident DPCG (cg_resident.cu) ----
+void resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *rowid_host);
+void resident_destroy(mgpu_ctx *c);
+void launch_cg_resident(mgpu_ctx *c, int l, int n);
 
 }  // namespace mgpu_int

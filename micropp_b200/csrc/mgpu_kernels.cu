@@ -1435,6 +1435,7 @@ void prof_drain(mgpu_ctx *c) {
         c->prof_acc[6] += ms;
         c->prof_acc[7] += e.slots;
         break;
+      case 5: c->prof_res_ms += ms; break;  // cluster-resident DPCG solves
       default: break;
     }
     c->ev_pool.push_back(e);
@@ -2198,14 +2199,35 @@ mgpu_ctx::StepGraph build_step_graph(mgpu_ctx *c, int B, int use_shared, int ls)
   const unsigned long long l0 = c->launches;
   cudaGraph_t g;
   CK(cudaGraphCreate(&g, 0));
-  cudaGraphConditionalHandle cond;
-  CK(cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
+  const bool resident = use_shared == OP_IMPLICIT && c->res != nullptr;
+  cudaGraphConditionalHandle cond = cudaGraphConditionalHandle();
+  // (a handle that no conditional node uses makes cudaGraphInstantiate fail: only the looping graphs create one)
+  if (!resident) CK(cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
 
   // head: Jacobian, CG start, CG list := Newton-list slots whose loop-head test says "iterate"
   capture_begin(c, g, nullptr, 0);
   c->dyn_count = cnt;
   if (use_shared == OP_SLOT) mgpu_asm_mat(c, LN, B, 0);
   if (use_shared == OP_HYBRID) mgpu_asm_mat_hyb(c, LN, B);
+  if (resident) {
+    // the whole DPCG solve of every slot is one cluster-resident kernel: no loop node, the tail follows in stream order
+    mgpu_cg_resident(c, LN, B);
+    mgpu_axpy_u(c, LN, B);
+    mgpu_asm_rhs(c, LN, B, 1);
+    k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[LN], 0, cnt, c->d_list[LN], cnt, nullptr, c->T, 0, cond, 0, nullptr);
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_count + 4 * ls, cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    capture_end(c);
+    mgpu_ctx::StepGraph sgr;
+    sgr.fixed_launches = (int)(c->launches - l0);
+    sgr.body_launches = 0;
+    c->dyn_count = nullptr;
+    c->launches = l0;  // captured, not executed
+    c->prof = prof;
+    CK(cudaGraphInstantiate(&sgr.exec, g, 0));
+    CK(cudaGraphDestroy(g));
+    return sgr;
+  }
   mgpu_cg_init(c, LN, B, use_shared);
   k_compact<<<1, 1024, 0, c->stream>>>(c->d_list[LN], 0, cnt, c->d_list[LC], cnt + 1, nullptr, c->T, 1, cond, 1,
                                        nullptr);
@@ -2640,6 +2662,13 @@ void mgpu_prof_read(mgpu_ctx *c, double *out9, int reset) {
   }
   if (reset)
     for (int i = 0; i < 8; ++i) c->prof_acc[i] = 0;
+}
+// accumulated time of the cluster-resident DPCG solves since the last reset (profiling mode)
+double mgpu_prof_resident_ms(mgpu_ctx *c, int reset) {
+  prof_drain(c);
+  const double ms = c->prof_res_ms;
+  if (reset) c->prof_res_ms = 0;
+  return ms;
 }
 void mgpu_timer_start(mgpu_ctx *c) { CK(cudaEventRecord(c->t0, c->stream)); }
 float mgpu_timer_stop(mgpu_ctx *c) {

@@ -1032,6 +1032,16 @@ unsigned long long micropp3x_launch_count(const micropp3 *s) {
 int micropp3x_implicit_kernel(const micropp3 *s) {
   return mgpu_implicit_kernel(mpp_access::engine((micropp<3> *)s->ptr)->ctx);
 }
+int micropp3x_resident_info(const micropp3 *s, int *meta8) {
+  int meta[8];
+  mgpu_resident_info(mpp_access::engine((micropp<3> *)s->ptr)->ctx, meta);
+  if (meta8)
+    for (int q = 0; q < 8; ++q) meta8[q] = meta[q];
+  return meta[0];
+}
+double micropp3x_prof_resident_ms(micropp3 *s, int reset) {
+  return mgpu_prof_resident_ms(mpp_access::engine((micropp<3> *)s->ptr)->ctx, reset);
+}
 double micropp3x_apply_operator(micropp3 *s, const double *p, double *Ap, int op, int kernel) {
   micropp<3> *m = (micropp<3> *)s->ptr;
   mpp_engine *e = mpp_access::engine(m);
@@ -1053,6 +1063,9 @@ double micropp3x_apply_operator(micropp3 *s, const double *p, double *Ap, int op
 }
 double micropp3x_bench_spmv(micropp3 *s, int nslots, int iters) {
   return mgpu_bench_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters);
+}
+double micropp3x_bench_resident(micropp3 *s, int nslots, int reps, int dbg) {
+  return mgpu_bench_resident(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, reps, dbg);
 }
 double micropp3x_bench_imp_spmv(micropp3 *s, int nslots, int iters, int kern) {
   return mgpu_bench_imp_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters, kern);

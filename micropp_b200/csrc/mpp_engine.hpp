@@ -27,6 +27,10 @@ struct mpp_engine {
   // DPCG on the slots of `list` (src/ell.cpp:66-122).  The loop condition is evaluated on the device
   // per slot; the host only learns how many slots are still iterating, every cg_chunk iterations.
   void cg_solve(int list, int n, int use_shared, bool generic = false) {
+    if (!generic && use_shared == 3 && mgpu_resident(ctx)) {  // the whole solve inside one cluster per RVE
+      mgpu_cg_resident(ctx, list, n);
+      return;
+    }
     mgpu_cg_init(ctx, list, n, generic ? 2 : use_shared);
     int cur = L_CG_A, other = L_CG_B;
     int nc = mgpu_compact(ctx, list, n, cur, 1);

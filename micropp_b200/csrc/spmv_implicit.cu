@@ -626,6 +626,7 @@ void mgpu_int::implicit_setup(mgpu_ctx *c, const mgpu_config *cfg, int *nblk_max
   V.rowid = to_device(c, rowid);
   c->nfix = 0;
   c->imp_kernel = IMP_SIMPLE;
+  resident_setup(c, cfg, rowid.data());  // whole solves inside one cluster when the RVE fits (cg_resident.cu)
   if (P.nx % 2 != 0) {
     // TMA needs 16-B global strides (nx even).  Said out loud, not chosen silently: an odd nx runs the table-driven
     // kernel, which is correct but L1-bound (1.12 ms instead of 0.6 ms per application of 1024 RVEs at 30^3)
@@ -667,6 +668,7 @@ void mgpu_int::implicit_setup(mgpu_ctx *c, const mgpu_config *cfg, int *nblk_max
 }
 
 void mgpu_int::implicit_destroy(mgpu_ctx *c) {
+  resident_destroy(c);
   if (c->V.rows) cudaFree((void *)c->V.rows);
   if (c->V.rkinv) cudaFree((void *)c->V.rkinv);
   if (c->V.rowid) cudaFree((void *)c->V.rowid);

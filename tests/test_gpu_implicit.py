@@ -14,12 +14,15 @@ pytestmark = pytest.mark.gpu
 def run(mod_cls, params, eps, implicit=None, kernel=None):
     """One homogenize() of a fresh object; implicit / kernel select the operator through the environment
     (MICROPP_IMPLICIT: 0 = one assembled ELL matrix per slot; MICROPP_IMP_KERNEL: 0 = k_spmv_dot_imp, the table-driven
-    multi-RHS kernel; unset = the default: k_spmv_dot_tmac + k_spmv_fix (TMA load and TMA store) when nx is even)."""
+    multi-RHS kernel, 3 = k_spmv_dot_tmac + k_spmv_fix (TMA load and TMA store) when nx is even -- both inside the
+    three-kernel DPCG loop (MICROPP_RESIDENT=0); unset = the default: the cluster-resident DPCG kernel whenever the RVE
+    fits a cluster, tests/test_gpu_resident.py)."""
     env = {}
     if implicit is not None:
         env["MICROPP_IMPLICIT"] = "1" if implicit else "0"
     if kernel is not None:
         env["MICROPP_IMP_KERNEL"] = str(kernel)
+        env["MICROPP_RESIDENT"] = "0"
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -57,11 +60,11 @@ def test_implicit_simple_kernel_equals_explicit_bitwise(mpp, dims, ngp):
         assert np.array_equal(gi.get_u(gp), ge.get_u(gp))
 
 
-@pytest.mark.parametrize("kernel", [None])
+@pytest.mark.parametrize("kernel", [None, 3])
 @pytest.mark.parametrize("dims,ngp", DIMS + [((16, 16, 16), 9), ((20, 10, 12), 2), ((30, 30, 30), 3), ((40, 18, 70), 2)])
 def test_implicit_tma_kernels_equal_explicit(mpp, dims, ngp, kernel):
-    """The default kernels (k_spmv_dot_tmac + k_spmv_fix when nx is even, else the table-driven kernel -- said on
-    stderr).  Ap is bit-identical (test_operator_application), p.Ap is summed in another fixed order, so the DPCG path
+    """kernel None: the default path (cluster-resident DPCG where the RVE fits); 3: the three-kernel loop with
+    k_spmv_dot_tmac + k_spmv_fix when nx is even, else the table-driven kernel -- said on stderr.  Ap is bit-identical (test_operator_application), p.Ap is summed in another fixed order, so the DPCG path
     differs by rounding.  DPCG stops at |z| < 1e-5 |z0| and amplifies rounding differences by about 1/tolerance x condition:
     cubic meshes stay below 1e-9, strongly anisotropic ones (dx != dy != dz) reach 1e-7 -- the same size as the
     difference between the assembled-matrix path and the reference CPU path on those meshes."""
