@@ -248,6 +248,38 @@ class Env:
         return self._red(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
 
 
+def resident_roofline(n, info, res_ms, prof, prof_ms, apps, nsteps, ngp):
+    """roofline of k_cg_resident: the WHOLE DPCG solve of an all-elastic RVE inside one thread-block cluster (operator,
+    dot products, vector updates; p and du in shared memory, r in registers).  Its bound is the FP64 pipe: a DPCG
+    iteration moves no HBM byte, a solve reads b and writes du (48 B per node).  `achieved` counts the ALGORITHMIC
+    flops of the operator (243 FMA per interior node and iteration) -- the kernel executes 153 of them for
+    mirror-symmetric row blocks, and about 42 more FMA per node for the dot products and vector updates."""
+    peak, peak_src = hbm_peak()
+    sec = max(res_ms, 1e-9) * 1e-3
+    nint, nn = (n - 2) ** 3, n ** 3
+    flops = 2.0 * 243.0 * nint * apps
+    tf = flops / sec / 1e12
+    solves = ngp * nsteps
+    hbm_bytes = 48.0 * nn * solves
+    return {"kernel": "k_cg_resident (whole DPCG solve: operator + dot products + vector updates of every iteration in "
+                      "ONE launch, one thread-block cluster per RVE; no HBM traffic inside the loop)",
+            "bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+            "peak_source": "nominal FP64: 148 SM x 64 DFMA/clk x 1965 MHz; a cluster of %d CTAs x %d clusters in flight "
+                           "occupies %d of the 148 SMs" % (info["cs"], info["clusters"], info["cs"] * info["clusters"]),
+            "flops_counted": "2 x 243 x interior nodes per DPCG iteration (the dense 27 x 3 x 3 stencil of SURVEY 8d); "
+                             "the kernel runs the 153 structurally non-zero terms of a mirror-symmetric row block",
+            "traffic": None, "rve_applications": apps, "launches": None, "kernel_ms": res_ms,
+            "share_of_step": res_ms / max(prof_ms, 1e-9), "instrumented_step_ms": prof_ms / nsteps,
+            "us_per_rve_iteration": res_ms * 1e3 / max(apps, 1.0),
+            "cluster": info,
+            "hbm": {"algorithmic_bytes_per_solve": 48.0 * nn, "achieved_gbs": hbm_bytes / sec / 1e9, "peak_gbs": peak,
+                    "peak_source": peak_src,
+                    "three_kernel_loop_bytes_per_rve_iteration": 248.0 * nn,
+                    "note": "the three-kernel loop (MICROPP_RESIDENT=0) streams 248 B per node and iteration; resident: 0"},
+            "other_kernels_ms": {"asm_mat": prof["asm_mat_ms"], "asm_rhs": prof["asm_rhs_ms"],
+                                 "cg_vectors": prof["cg_vec_ms"]}}
+
+
 def spmv_roofline(name, n, prof, prof_ms, apps, implicit_kernel, nsteps, vec_apps=None):
     """roofline of the DPCG SpMV (+ the DPCG vector kernels) from the instrumented repeat (CUDA events per launch)"""
     peak, peak_src = hbm_peak()
@@ -409,6 +441,8 @@ def run_b200_workload(M, env: Env, name: str, ngp: int, steps: int, warmup: int,
         lib.micropp3_homogenize(h)
         prof_dev_ms += m.last_homogenize_ms()
     prof = m.prof_read(True)
+    res_ms = m.prof_resident_ms(True)   # cluster-resident DPCG solves (one launch per Newton step and wave)
+    res_info = m.resident_info()
     m.prof_enable(False)
 
     dev_ms_max = env.max(dev_ms)
@@ -442,8 +476,11 @@ def run_b200_workload(M, env: Env, name: str, ngp: int, steps: int, warmup: int,
                            "frac": h_flop / (max(h_ms, 1e-9) * 1e-3) / 1e12 / FP64_PEAK_TFLOPS},
                   "assembled_equivalent_gbs": spmv_bytes_per_rve(n)[0] * h_apps / (max(h_ms, 1e-9) * 1e-3) / 1e9}
         apps = float(prof["spmv_slot_apps"])
-    roof = spmv_roofline(name, n, prof, prof_dev_ms, apps, imp_kernel, steps,
-                         vec_apps=apps + float(prof["hybrid_slot_apps"]))
+    if res_info is not None and res_ms > 0.0:
+        roof = resident_roofline(n, res_info, res_ms, prof, prof_dev_ms, apps, steps, ngp)
+    else:
+        roof = spmv_roofline(name, n, prof, prof_dev_ms, apps, imp_kernel, steps,
+                             vec_apps=apps + float(prof["hybrid_slot_apps"]))
     if hybrid is not None:
         if prof["hybrid_spmv_ms"] > prof["spmv_ms"]:
             # the hybrid operator is the dominant kernel of this step: it is the roofline entry, the fully assembled

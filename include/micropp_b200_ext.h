@@ -133,6 +133,8 @@ double micropp3x_bench_spmv(struct micropp3 *self, int nslots, int iters); /* ms
 double micropp3x_bench_imp_spmv(struct micropp3 *self, int nslots, int iters, int kern);
 /* isolated timing of the cluster-resident DPCG kernel (mgpu_bench_resident); ms per launch, -1 when unavailable */
 double micropp3x_bench_resident(struct micropp3 *self, int nslots, int reps, int dbg);
+/* per-warp phase cycle counters of the last dbg-256 run of slot `slot`: [8 CTAs][16 warps][8 phases] */
+void micropp3x_resident_timeline(struct micropp3 *self, int slot, long long *out1024);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,7 @@ def load():
         "micropp3x_bench_spmv": (C.c_double, [H, C.c_int, C.c_int]),
         "micropp3x_bench_imp_spmv": (C.c_double, [H, C.c_int, C.c_int, C.c_int]),
         "micropp3x_bench_resident": (C.c_double, [H, C.c_int, C.c_int, C.c_int]),
+        "micropp3x_resident_timeline": (None, [H, C.c_int, C.POINTER(C.c_longlong)]),
         "material_set": (None, [C.POINTER(MaterialBase), C.c_int] + [C.c_double] * 5),
         "mgpu_device_count": (C.c_int, []),
     }
@@ -405,6 +406,12 @@ class Micropp3:
     def bench_resident(self, nslots, reps=3, dbg=4):
         """ms per isolated launch of the cluster-resident DPCG kernel over nslots RVEs (dbg bit 4: exactly 60 iterations)."""
         return float(self.lib.micropp3x_bench_resident(C.byref(self.h), int(nslots), int(reps), int(dbg)))
+
+    def resident_timeline(self, slot=0):
+        """[8 CTAs][16 warps][8 phases] cycle counters of the last bench_resident(..., dbg | 256) run."""
+        out = np.zeros(1024, dtype=np.int64)
+        self.lib.micropp3x_resident_timeline(C.byref(self.h), int(slot), out.ctypes.data_as(C.POINTER(C.c_longlong)))
+        return out.reshape(8, 16, 8)
 
     def bench_imp_spmv(self, nslots, iters=20, kern=2):
         """ms per application of the implicit elastic operator on `nslots` RVEs (kern: 2 context default, 10+v TMA variant v)."""

@@ -29,7 +29,8 @@ namespace mgpu_int {
 constexpr int RES_MAX_CS = 8;
 constexpr int RES_SMEM_LIMIT = 232448;  // 227 KB: the opt-in dynamic shared memory of one sm_100 CTA
 constexpr int RES_MAX_PAIRS = 3;        // unordered material pairs {a < b}: u = a + b - 1, table D_u = Ke_b - Ke_a
-constexpr int RES_MAX_GROUPS = 16;      // interface entries per CTA <= 32 * RES_MAX_GROUPS
+constexpr int RES_MAX_GROUPS = 16;      // interface entries per CTA <= RES_GROUP * RES_MAX_GROUPS (2 pieces per group: 32 bits)
+constexpr int RES_GROUP = 32;           // entries of an interface group: one per lane
 constexpr int RES_DLEN = 8 * 8 * 9;     // doubles of one difference table: [element position][element node][3x3]
 
 // the difference tables (Ke_t - Ke_m) of the pairs, passed BY VALUE as a __grid_constant__ kernel parameter like the
@@ -51,14 +52,16 @@ struct ResGeom {
   int ntask[RES_MAX_CS], taskcap;  // halo rows to push after every p update
   int y0[RES_MAX_CS], y1[RES_MAX_CS], z0[RES_MAX_CS], z1[RES_MAX_CS];  // owned INTERIOR (0-based) row ranges
   int nfix[RES_MAX_CS];
-  int off_du, off_r2, off_task, off_fixe, off_fixk, off_fixout, off_red, off_wp, smem_bytes;
+  int off_du, off_r2, off_task, off_time, off_fixe, off_fixk, off_fixout, off_red, off_wp, smem_bytes;
   double rkp[3][3];    // 1 / diagonal of the three pure-material row blocks (the Jacobi preconditioner of most nodes)
   const int4 *tinfo;   // [cs][nthreads]  x: ly | lz << 8 | chunk << 16 | material << 24 (-1: idle thread)
                        //                 y: valid-node mask | interface-node mask << 8, z: first interface entry,
                        //                 w: own row | (interface groups this thread's WARP computes) << 16
   const int4 *fixe;    // [cs][fixcap]    x: ly | lz << 8 | i << 16, y: 8 codes of 3 bits, one per element position (0: element
                        //                 of the chunk's material m; else (1 + u) | neg << 2 for an element of type t: u the
-                       //                 pair {m, t}, neg = t < m, i.e. the correction is -D_u), z: row-block id
+                       //                 pair {m, t}, neg = t < m, i.e. the correction is -D_u), z: row-block id,
+                       //                 w: position in owner order (the list itself is in bank-aware work order)
+  const unsigned *wpiece;  // [cs][16]       interface pieces of every warp: bit 2 g + h = element positions 4 h .. 4 h + 3 of group g
   const int2 *task;    // [cs][taskcap]   x: brick offset of the own row (node i = 1, component 0), y: destination rank
                        //                 << 24 | brick offset of its halo copy there
 };
@@ -132,6 +135,7 @@ namespace {
 struct ResPlan {
   ResGeom g;
   std::vector<int4> tinfo, fixe;
+  std::vector<unsigned> wpiece;
   std::vector<int2> task;
   bool ok = false;
 };
@@ -255,30 +259,90 @@ bool res_plan_try(int nx, int ny, int nz, const int *elem_type, const int *rowid
       out.tinfo[(size_t)r * G.nthreads + tid] =
           make_int4(ly | (lz << 8) | (c << 16) | (m << 24), ((1 << nv) - 1) | (fixmask << 8), fixbase, rr);
     }
+    // Work order of the interface entries (w = position in owner order, where the owner thread looks its correction and
+    // its 1 / diagonal up).  Every shared load of the interface pass sits at a fixed offset from the entry's node, so
+    // 16 lanes (a half-warp) whose NODES fall into 16 different 8-B banks are conflict-free in all of them.
+    {
+      // groups of RES_GROUP: entries sorted by the set of element positions they need (a warp executes a position if ANY of its
+      // lanes needs it), so the groups skip most positions; inside a group the half-warps are packed by bank
+      std::vector<int4> sorted;
+      for (int q = 0; q < (int)fix[r].size(); ++q) {
+        int4 e = fix[r][q];
+        e.w = q;
+        sorted.push_back(e);
+      }
+      auto posmask = [](const int4 &e) {
+        int m8 = 0;
+        for (int c = 0; c < 8; ++c)
+          if (((unsigned)e.y >> (3 * c)) & 7u) m8 |= 1 << c;
+        return m8;
+      };
+      std::stable_sort(sorted.begin(), sorted.end(), [&](const int4 &a, const int4 &b) {
+        const int ma = posmask(a), mb = posmask(b);
+        const int pa = __builtin_popcount(ma), pb = __builtin_popcount(mb);
+        return pa != pb ? pa < pb : ma < mb;
+      });
+      std::vector<int4> order;
+      for (size_t g0 = 0; g0 < sorted.size(); g0 += RES_GROUP) {
+        const size_t g1 = std::min(sorted.size(), g0 + RES_GROUP);
+        std::vector<std::vector<int4>> bybank(16);
+        for (size_t q = g0; q < g1; ++q) {
+          const int4 &e = sorted[q];
+          const int no = ((e.x >> 8) & 0xff) * G.zp + (e.x & 0xff) * G.pitch + (e.x >> 16);
+          bybank[no & 15].push_back(e);
+        }
+        size_t left = g1 - g0;
+        while (left > 0) {
+          int taken = 0;
+          for (int b = 0; b < 16 && taken < 16; ++b)
+            if (!bybank[b].empty()) {
+              order.push_back(bybank[b].back());
+              bybank[b].pop_back();
+              ++taken;
+              --left;
+            }
+          while (taken < 16 && left > 0) {  // fill the half-warp with whatever is left (conflicts, but no idle lanes)
+            int bb = 0;
+            for (int b = 1; b < 16; ++b)
+              if (bybank[b].size() > bybank[bb].size()) bb = b;
+            order.push_back(bybank[bb].back());
+            bybank[bb].pop_back();
+            ++taken;
+            --left;
+          }
+        }
+      }
+      fix[r] = order;
+    }
     G.nfix[r] = (int)fix[r].size();
     G.fixcap = std::max(G.fixcap, G.nfix[r]);
-    if (G.nfix[r] > 32 * RES_MAX_GROUPS || nyr * (G.z1[r] - G.z0[r]) > 0xffff) return false;
-    // groups of 32 interface entries -> warps: the FP64 pipe belongs to a quarter of the SM (warp w runs on quarter
-    // w % 4), so the groups go to the least loaded quarter (an operator pass counts 1, a group 0.35), then to its
-    // least loaded warp
-    std::vector<double> wload(G.nwarps, 0.0);
-    std::vector<int> gmask(G.nwarps, 0);
-    for (int w = 0; w < G.nwarps; ++w)
-      for (int l = 0; l < 32; ++l)
-        if (w * 32 + l < (int)items[r].size() && items[r][w * 32 + l].m >= 0) wload[w] = 1.0;
-    for (int g = 0; g * 32 < G.nfix[r]; ++g) {
-      double q4[4] = {0, 0, 0, 0};
-      for (int w = 0; w < G.nwarps; ++w) q4[w % 4] += wload[w];
-      int bq = 0;
-      for (int q = 1; q < std::min(4, G.nwarps); ++q)
-        if (q4[q] < q4[bq]) bq = q;
-      int bw = bq;
-      for (int w = bq; w < G.nwarps; w += 4)
-        if (wload[w] < wload[bw]) bw = w;
-      wload[bw] += 0.35;
-      gmask[bw] |= 1 << g;
+    if (G.nfix[r] > RES_GROUP * RES_MAX_GROUPS || G.nwarps > 16 || nyr * (G.z1[r] - G.z0[r]) > 0xffff) return false;
+    // Interface PIECES -> warps.  A piece = (group of 32 entries, half of the 8 element positions): about 0.4 of an
+    // operator pass in issued instructions, whatever the number of active lanes.  A warp that computed a whole group on
+    // top of its operator pass was the straggler of its CTA and of the cluster (15 k cycles per group against 8 - 13 k
+    // for the operator pass, measured per warp with clock64); the pieces level the four SM quarters instead (warp w
+    // issues on quarter w % 4; an operator pass counts 1).
+    {
+      std::vector<double> wload(G.nwarps, 0.0);
+      std::vector<unsigned> pm(16, 0u);
+      for (int w = 0; w < G.nwarps; ++w)
+        for (int l = 0; l < 32; ++l)
+          if (w * 32 + l < (int)items[r].size() && items[r][w * 32 + l].m >= 0) wload[w] = 1.0;
+      for (int pc = 0; pc < 2 * ((G.nfix[r] + RES_GROUP - 1) / RES_GROUP); ++pc) {
+        double q4[4] = {0, 0, 0, 0};
+        for (int w = 0; w < G.nwarps; ++w) q4[w % 4] += wload[w];
+        int bq = 0;
+        for (int q = 1; q < std::min(4, G.nwarps); ++q)
+          if (q4[q] < q4[bq]) bq = q;
+        int bw = bq;
+        for (int w = bq; w < G.nwarps; w += 4)
+          if (wload[w] < wload[bw]) bw = w;
+        wload[bw] += 0.4;
+        pm[bw] |= 1u << pc;
+      }
+      if (out.wpiece.empty()) out.wpiece.assign((size_t)cs * 16, 0u);
+      for (int w = 0; w < 16; ++w) out.wpiece[(size_t)r * 16 + w] = pm[w];
     }
-    for (int tid = 0; tid < G.nthreads; ++tid) out.tinfo[(size_t)r * G.nthreads + tid].w |= gmask[tid / 32] << 16;
   }
   out.fixe.assign((size_t)cs * std::max(G.fixcap, 1), make_int4(0, 0, 0, 0));
   for (int r = 0; r < cs; ++r) std::copy(fix[r].begin(), fix[r].end(), out.fixe.begin() + (size_t)r * G.fixcap);
@@ -311,12 +375,14 @@ bool res_plan_try(int nx, int ny, int nz, const int *elem_type, const int *rowid
   if (G.nthreads > 384) off += up(sizeof(double) * G.dstride);
   G.off_task = (int)off;
   off += up(sizeof(int2) * G.taskcap);
+  G.off_time = (int)off;
+  off += up(sizeof(long long) * 16 * 9);  // phase counters of the timeline instrument (dbg bit 256)
   G.off_fixe = (int)off;
   off += up(sizeof(int4) * G.fixcap);
   G.off_fixk = (int)off;
   off += up(sizeof(double) * 3 * G.fixcap);
   G.off_fixout = (int)off;
-  off += up(sizeof(double) * 3 * G.fixcap);
+  off += up(sizeof(double) * 2 * 3 * G.fixcap);  // [half][entry][3]
   G.off_red = (int)off;
   off += up(sizeof(double) * 2 * 2 * RES_MAX_CS);
   G.off_wp = (int)off;
@@ -420,43 +486,93 @@ __device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp,
   }
 }
 
-// the thread's TN nodes x 3 rows of A_m p: 9 neighbour rows x 3 components x (TN + 2) 64-bit shared loads, 243 TN DFMAs
-// whose row-block operand is a uniform register (kernel parameter)
-template <int MAT, int TN>
+// The thread's TN nodes x 3 rows of A_m p: 9 neighbour rows x 3 components x (TN + 2) 64-bit shared loads, DFMAs whose
+// row-block operand is a uniform register (kernel parameter).
+// SPARSE: a pure-material row block of an axis-aligned orthotropic (e.g. isotropic) material on the regular grid is
+// mirror-symmetric, so the coupling of components fi != fj towards the neighbour at offset o vanishes unless o_fi != 0
+// and o_fj != 0: 153 of the 243 entries are structurally non-zero (verified on the actual row blocks at set-up; the
+// dense copy runs otherwise).  The 9 neighbour rows (oy, oz) fall into 4 classes with the same pattern -- oy, oz zero
+// or not -- and each class is a rolled loop over its rows with a compile-time body: 9 / 13 / 13 / 23 DFMAs per node.
+template <int MAT, int TN, bool OY, bool OZ>
+__device__ __forceinline__ void res_apply_row(const PureRows &R, const double *__restrict__ rb, int row, int cstride,
+                                              double (&acc)[TN][3]) {
+#pragma unroll
+  for (int fj = 0; fj < 3; ++fj) {
+    double pv[TN + 2];
+#pragma unroll
+    for (int h = 0; h < TN + 2; ++h) pv[h] = rb[fj * cstride + h];
+#pragma unroll
+    for (int di = 0; di < 3; ++di) {
+      const double *a = &R.a[MAT * RB_LEN + (row * 3 + di) * RB_NBR];
+      const bool ox = di != 1;
+#pragma unroll
+      for (int fi = 0; fi < 3; ++fi) {
+        // offsets of the neighbour along the axes of fi and fj
+        const bool ofi = fi == 0 ? ox : fi == 1 ? OY : OZ, ofj = fj == 0 ? ox : fj == 1 ? OY : OZ;
+        if (fi != fj && !(ofi && ofj)) continue;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) acc[t][fi] += a[fi * 3 + fj] * pv[t + di];
+      }
+    }
+  }
+}
+
+template <int MAT, int TN, bool SPARSE>
 __device__ __forceinline__ void res_apply(const PureRows &R, const double *__restrict__ brick, int base, int pitch,
                                           int zp, int cstride, double (&acc)[TN][3]) {
+  if (SPARSE) {
+    res_apply_row<MAT, TN, false, false>(R, brick + base + zp + pitch, 4, cstride, acc);  // (oy, oz) = (0, 0)
 #pragma unroll 1
-  for (int row = 0; row < 9; ++row) {
-    const int dk = row / 3, dj = row - dk * 3;
-    const double *rb = brick + base + dk * zp + dj * pitch;
+    for (int q = 0; q < 2; ++q) {  // oy != 0, oz = 0: rows 3 and 5
+      const int row = 3 + 2 * q;
+      res_apply_row<MAT, TN, true, false>(R, brick + base + zp + (2 * q) * pitch, row, cstride, acc);
+    }
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {  // oy = 0, oz != 0: rows 1 and 7
+      const int row = 1 + 6 * q;
+      res_apply_row<MAT, TN, false, true>(R, brick + base + (2 * q) * zp + pitch, row, cstride, acc);
+    }
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {  // oy != 0, oz != 0: rows 0, 2, 6, 8
+      const int dk = 2 * (q >> 1), dj = 2 * (q & 1);
+      res_apply_row<MAT, TN, true, true>(R, brick + base + dk * zp + dj * pitch, dk * 3 + dj, cstride, acc);
+    }
+  } else {
+#pragma unroll 1
+    for (int row = 0; row < 9; ++row) {
+      const int dk = row / 3, dj = row - dk * 3;
+      const double *rb = brick + base + dk * zp + dj * pitch;
 #pragma unroll
-    for (int fj = 0; fj < 3; ++fj) {
-      double pv[TN + 2];
+      for (int fj = 0; fj < 3; ++fj) {
+        double pv[TN + 2];
 #pragma unroll
-      for (int h = 0; h < TN + 2; ++h) pv[h] = rb[fj * cstride + h];
+        for (int h = 0; h < TN + 2; ++h) pv[h] = rb[fj * cstride + h];
 #pragma unroll
-      for (int di = 0; di < 3; ++di) {
-        const double *a = &R.a[MAT * RB_LEN + (row * 3 + di) * RB_NBR];
+        for (int di = 0; di < 3; ++di) {
+          const double *a = &R.a[MAT * RB_LEN + (row * 3 + di) * RB_NBR];
 #pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const double pval = pv[t + di];
-          acc[t][0] += a[fj] * pval;
-          acc[t][1] += a[3 + fj] * pval;
-          acc[t][2] += a[6 + fj] * pval;
+          for (int t = 0; t < TN; ++t) {
+            const double pval = pv[t + di];
+            acc[t][0] += a[fj] * pval;
+            acc[t][1] += a[3 + fj] * pval;
+            acc[t][2] += a[6 + fj] * pval;
+          }
         }
       }
     }
   }
 }
 
-// Interface pass of one group of 32 entries (one per lane; `on`: the lane holds an entry): for every pair that occurs in
-// the warp and every element position some lane needs, the lanes that need it add (Ke_t - Ke_m)[node rows] . p(element
-// nodes): 72 DFMAs whose coefficient is a uniform register (kernel parameter), 24 shared loads of p.
-__device__ __forceinline__ void res_fix_group(const ResDtab &DT, const double *__restrict__ brick, int no, int pitch,
-                                              int zp, int cstride, unsigned codes, bool on, double (&yout)[3]) {
+// Interface pass of one PIECE: 32 entries (one per lane; `on`: the lane holds an entry) x the element positions
+// 4 half .. 4 half + 3.  For every pair that occurs in the warp and every position of the half that some lane needs,
+// the lanes that need it add (Ke_t - Ke_m)[node rows] . p(element nodes): 72 DFMAs whose coefficient is a uniform
+// register (kernel parameter at a compile-time address), 24 shared loads of p.
+__device__ __forceinline__ void res_fix_piece(const ResDtab &DT, const double *__restrict__ brick, int no, int pitch,
+                                              int zp, int cstride, unsigned codes, bool on, int half, double (&yout)[3]) {
   yout[0] = yout[1] = yout[2] = 0.0;
 #pragma unroll
   for (int pr = 0; pr < RES_MAX_PAIRS; ++pr) {  // unrolled: the table entries are compile-time constant-bank addresses
+                                                // (rolled, the coefficients came through indexed LDC: 5 x slower)
     unsigned m8 = 0, neg = 0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -467,13 +583,16 @@ __device__ __forceinline__ void res_fix_group(const ResDtab &DT, const double *_
       }
     }
     if (!on) m8 = 0;
+    m8 &= 0xfu << (4 * half);
     const unsigned any8 = __reduce_or_sync(0xffffffffu, m8);
     if (!any8) continue;
-    double y[3] = {0.0, 0.0, 0.0};
+    double y[4][3];  // 12 independent accumulation chains
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q][0] = y[q][1] = y[q][2] = 0.0;
     const double *Dp = &DT.d[pr][0];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      if (!((any8 >> c) & 1)) continue;  // warp-uniform
+      if (!((any8 >> c) & 1)) continue;  // warp-uniform (also skips the other half)
       if ((m8 >> c) & 1) {
         const int ax = (c >> 2) & 1, ay = (c >> 1) & 1, az = c & 1;
         const int eo = no + (az - 1) * zp + (ay - 1) * pitch + (ax - 1);  // first node of the element
@@ -482,22 +601,22 @@ __device__ __forceinline__ void res_fix_group(const ResDtab &DT, const double *_
           const int q = eo + corner_z(jn) * zp + corner_y(jn) * pitch + corner_x(jn);
           const double p0 = brick[q], p1 = brick[cstride + q], p2 = brick[2 * cstride + q];
           const double *d = Dp + (c * 8 + jn) * 9;
-          y[0] += d[0] * p0;
-          y[1] += d[3] * p0;
-          y[2] += d[6] * p0;
-          y[0] += d[1] * p1;
-          y[1] += d[4] * p1;
-          y[2] += d[7] * p1;
-          y[0] += d[2] * p2;
-          y[1] += d[5] * p2;
-          y[2] += d[8] * p2;
+          double(&yy)[3] = y[jn & 3];
+          yy[0] += d[0] * p0;
+          yy[1] += d[3] * p0;
+          yy[2] += d[6] * p0;
+          yy[0] += d[1] * p1;
+          yy[1] += d[4] * p1;
+          yy[2] += d[7] * p1;
+          yy[0] += d[2] * p2;
+          yy[1] += d[5] * p2;
+          yy[2] += d[8] * p2;
         }
       }
     }
     const double sg = neg ? -1.0 : 1.0;
-    yout[0] += sg * y[0];
-    yout[1] += sg * y[1];
-    yout[2] += sg * y[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) yout[d] += sg * ((y[0][d] + y[1][d]) + (y[2][d] + y[3][d]));
   }
 }
 
@@ -524,7 +643,7 @@ struct ResThread {
   double r[TN][RSM ? 2 : 3];
   double kk[3];
   double *s_p, *s_du, *s_r2;
-  const volatile double *s_fixk;
+  const double *s_fixk;
   int cstride, dstride, fixmask;
 
   __device__ __forceinline__ double r_get(int t, int d) const { return (RSM && d == 2) ? s_r2[t] : r[t][RSM ? (d & 1) : d]; }
@@ -534,26 +653,40 @@ struct ResThread {
     else
       r[t][RSM ? (d & 1) : d] = v;
   }
-  // 1 / diagonal of node t, component d; fi = number of interface nodes of the thread before t
-  template <bool FIX>
-  __device__ __forceinline__ double kinv(int t, int d, int fi) const {
-    return (FIX && ((fixmask >> t) & 1)) ? s_fixk[fi * 3 + d] : kk[d];
+  // The 1 / diagonal table of the interface nodes behind a pointer the compiler cannot trace: taken anew at the head of
+  // every phase, the loads of a phase are ordinary (batched) loads but cannot be hoisted out of the DPCG loop, where the
+  // 3 TN selected values would be spilled to local memory.
+  __device__ __forceinline__ const double *fixk_now() const {
+    const double *q = s_fixk;
+    asm volatile("" : "+l"(q));
+    return q;
   }
+  // 1 / diagonal of the thread's TN nodes, component d (one batch of loads per component: 2 TN registers)
   template <bool FIX>
-  __device__ __forceinline__ void init(const double (&bv)[TN][3], double &rzs, double &zzs) {
+  __device__ __forceinline__ void kinv(const double *fk, int d, double (&kd)[TN]) const {
     int fi = 0;
 #pragma unroll
     for (int t = 0; t < TN; ++t) {
+      const bool isfix = FIX && ((fixmask >> t) & 1);
+      kd[t] = isfix ? fk[fi * 3 + d] : kk[d];
+      if (isfix) ++fi;
+    }
+  }
+  template <bool FIX>
+  __device__ __forceinline__ void init(const double (&bv)[TN][3], double &rzs, double &zzs) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < 3; ++d) {
+      double kd[TN];
+      kinv<FIX>(fixk_now(), d, kd);
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {
         const double rv = bv[t][d];
-        const double z = __dmul_rn(kinv<FIX>(t, d, fi), rv);
+        const double z = __dmul_rn(kd[t], rv);
         r_set(t, d, rv);
         rzs += rv * z;
         zzs += z * z;
         s_p[d * cstride + t] = z;
       }
-      if (FIX && ((fixmask >> t) & 1)) ++fi;
     }
   }
   __device__ __forceinline__ double p_dot(const double (&acc)[TN][3]) const {
@@ -573,46 +706,62 @@ struct ResThread {
   __device__ __forceinline__ void update(const double (&acc)[TN][3], double alpha, double &zzs, double &rzs) {
     zzs = 0.0;
     rzs = 0.0;
-    int fi = 0;
 #pragma unroll
-    for (int t = 0; t < TN; ++t) {
+    for (int d = 0; d < 3; ++d) {
+      double kd[TN], rr[TN];
+      kinv<FIX>(fixk_now(), d, kd);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double rv = r_get(t, d) - alpha * acc[t][d];
+      for (int t = 0; t < TN; ++t) rr[t] = r_get(t, d);
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {
+        const double rv = rr[t] - alpha * acc[t][d];
         r_set(t, d, rv);
-        const double z = __dmul_rn(kinv<FIX>(t, d, fi), rv);
+        const double z = __dmul_rn(kd[t], rv);
         zzs += z * z;
         rzs += rv * z;
       }
-      if (FIX && ((fixmask >> t) & 1)) ++fi;
     }
   }
+  // (the loads of a component go out together before its stores: the compiler cannot reorder them itself, the three
+  // arrays might alias)
   __device__ __forceinline__ void du_update(double alpha) {
 #pragma unroll
-    for (int t = 0; t < TN; ++t)
+    for (int d = 0; d < 3; ++d) {
+      double pp[TN], du[TN];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) s_du[d * dstride + t] = fma(alpha, s_p[d * cstride + t], s_du[d * dstride + t]);
+      for (int t = 0; t < TN; ++t) {
+        pp[t] = s_p[d * cstride + t];
+        du[t] = s_du[d * dstride + t];
+      }
+#pragma unroll
+      for (int t = 0; t < TN; ++t) s_du[d * dstride + t] = fma(alpha, pp[t], du[t]);
+    }
   }
   template <bool FIX>
   __device__ __forceinline__ void p_update(double alpha, double beta) {
-    int fi = 0;
 #pragma unroll
-    for (int t = 0; t < TN; ++t) {
+    for (int d = 0; d < 3; ++d) {
+      double pp[TN], du[TN], rr[TN], kd[TN];
+      kinv<FIX>(fixk_now(), d, kd);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double pp = s_p[d * cstride + t];
-        s_du[d * dstride + t] = fma(alpha, pp, s_du[d * dstride + t]);
-        const double z = __dmul_rn(kinv<FIX>(t, d, fi), r_get(t, d));
-        s_p[d * cstride + t] = z + beta * pp;
+      for (int t = 0; t < TN; ++t) {
+        pp[t] = s_p[d * cstride + t];
+        du[t] = s_du[d * dstride + t];
+        rr[t] = r_get(t, d);
       }
-      if (FIX && ((fixmask >> t) & 1)) ++fi;
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {
+        s_du[d * dstride + t] = fma(alpha, pp[t], du[t]);
+        const double z = __dmul_rn(kd[t], rr[t]);
+        s_p[d * cstride + t] = z + beta * pp[t];
+      }
     }
   }
 };
 
 // Registers: the register file is 4 x 16384 (one quarter per SM sub-partition, warps are dealt round-robin), so a block
 // of 13..16 warps puts 4 warps on a quarter: 128 registers per thread (MAXT = 512); up to 12 warps leave 168 (MAXT = 384).
-template <int TN, int MAXT>
+template <int TN, int MAXT, bool SPARSE>
 __global__ void __launch_bounds__(MAXT, 1)
     k_cg_resident(const __grid_constant__ MeshConst P, const Lst L, int n_list, SlotTables T, VecPool V,
                   const __grid_constant__ ResGeom G, const __grid_constant__ PureRows R,
@@ -623,9 +772,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   double *s_r2 = reinterpret_cast<double *>(s_raw + G.off_r2);  // [nrows_max][dpitch], MAXT = 512 only
   int2 *s_task = reinterpret_cast<int2 *>(s_raw + G.off_task);
   int4 *s_fixe = reinterpret_cast<int4 *>(s_raw + G.off_fixe);
-  // volatile: the 1 / diagonal of an interface node is re-read where it is used -- hoisted out of the loop the 3 TN
-  // selected values would be spilled to local memory
-  volatile double *s_fixk = reinterpret_cast<volatile double *>(s_raw + G.off_fixk);
+  double *s_fixk = reinterpret_cast<double *>(s_raw + G.off_fixk);
   double *s_fixout = reinterpret_cast<double *>(s_raw + G.off_fixout);
   double *s_redA = reinterpret_cast<double *>(s_raw + G.off_red);
   double *s_redB = s_redA + 2 * RES_MAX_CS;
@@ -652,13 +799,13 @@ __global__ void __launch_bounds__(MAXT, 1)
     const int4 e = __ldg(&G.fixe[(size_t)rank * G.fixcap + q]);
     s_fixe[q] = e;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) s_fixk[q * 3 + d] = __ldg(&V.rkinv[e.z * 3 + d]);
+    for (int d = 0; d < 3; ++d) s_fixk[e.w * 3 + d] = __ldg(&V.rkinv[e.z * 3 + d]);
   }
   const int4 ti = __ldg(&G.tinfo[(size_t)rank * G.nthreads + tid]);
   const bool has = ti.x >= 0;
   const int ly = ti.x & 0xff, lz = (ti.x >> 8) & 0xff, ch = (ti.x >> 16) & 0xff, mat = has ? (ti.x >> 24) & 0x3 : 0;
   const int vmask = has ? (ti.y & 0xff) : 0, fixmask = has ? ((ti.y >> 8) & 0xff) : 0, fixbase = ti.z;
-  const unsigned gmask = (unsigned)ti.w >> 16;  // interface groups of this warp (the same for its 32 threads)
+  const unsigned pmask = __ldg(&G.wpiece[rank * 16 + (tid >> 5)]);  // interface pieces of this warp
   const int i0 = ch * TN + 1;
   const int po = has ? lz * zp + ly * pitch + i0 : G.nzb * zp;  // own first node, component 0 of the brick (idle: scratch row)
   const int dof = has ? (ti.w & 0xffff) * G.dpitch + ch * TN : G.nrows_max * G.dpitch;  // own first node in du
@@ -689,6 +836,8 @@ __global__ void __launch_bounds__(MAXT, 1)
   th.fixmask = fixmask;
 #pragma unroll
   for (int d = 0; d < 3; ++d) th.kk[d] = kk[d];
+  // warp-uniform choice of the phase copies: a warp with an interface node takes the <true> copy as a whole
+  const bool wfix = __any_sync(0xffffffffu, fixmask != 0);
   double s0 = 0.0, s1 = 0.0;
   {
     const size_t gnode = vo + (size_t)(G.z0[rank] + lz) * P.nxny + (size_t)(G.y0[rank] + ly) * P.nx + i0;
@@ -697,7 +846,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     for (int t = 0; t < TN; ++t)
 #pragma unroll
       for (int d = 0; d < 3; ++d) bv[t][d] = ((vmask >> t) & 1) ? V.b[gnode + (size_t)d * P.nn_pad + t] : 0.0;
-    if (fixmask)
+    if (wfix)
       th.template init<true>(bv, s0, s1);
     else
       th.template init<false>(bv, s0, s1);
@@ -713,44 +862,71 @@ __global__ void __launch_bounds__(MAXT, 1)
   if (hist_k > 0) hist[0] = pn;
   bool active = (0 < P.cg_max_its) && !(pn < P.cg_abs_tol || pn < pn * P.cg_rel_tol);  // src/ell.cpp:93-94
 
+  // dbg bit 256 (tools/resident_timeline.py): per-warp cycle counters of the phases of an iteration, summed over the
+  // solve and left in the slot's partial-sum buffer: [rank][warp][8] = interface pass, operator, wait for the block,
+  // cluster barrier A, update, cluster barrier B, du / p update + push, cluster barrier C
+  // (the counters live in shared memory: in registers they cost 18 registers of every thread, timing or not)
+  const bool timing = (dbg & 256) != 0;
+  long long *s_time = reinterpret_cast<long long *>(s_raw + G.off_time) + (tid >> 5) * 9;  // [warp][8 phases + last]
+  if (timing && (tid & 31) == 0)
+    for (int k = 0; k < 9; ++k) s_time[k] = 0;
+  auto lap = [&](int k) {
+    if (timing && (tid & 31) == 0) {
+      const long long now = clock64();
+      if (k >= 0) s_time[k] += now - s_time[8];
+      s_time[8] = now;
+    }
+  };
   while (active) {
+    lap(-1);
     // ---- Ap = A p ----
+    // interface corrections first: the few warps that compute a group start with it while the other warps are already in
+    // their operator pass, so its latency-bound instruction stream fills bubbles instead of running alone at the end
+    auto fix_pass = [&]() {
+      unsigned pm = pmask;
+      while (pm) {  // warp-uniform
+        const int pc = __ffs(pm) - 1, half = pc & 1;
+        pm &= pm - 1;
+        const int e = (pc >> 1) * 32 + (tid & 31);
+        const bool on = e < nfix;
+        const int4 fe = on ? s_fixe[e] : make_int4(0, 0, 0, 0);
+        const int no = ((fe.x >> 8) & 0xff) * zp + (fe.x & 0xff) * pitch + (fe.x >> 16);
+        double y[3];
+        res_fix_piece(DT, s_p, no, pitch, zp, cstride, (unsigned)fe.y, on, half, y);
+        if (on) {
+          double *o = s_fixout + (half * G.fixcap + fe.w) * 3;
+          o[0] = y[0];
+          o[1] = y[1];
+          o[2] = y[2];
+        }
+      }
+    };
+    const bool dofix = nfix > 0 && !(dbg & 1);  // CTA-uniform
+    if (dofix) fix_pass();
+    lap(0);
     double acc[TN][3];
 #pragma unroll
     for (int t = 0; t < TN; ++t) acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
     if (has && !(dbg & 8)) {
       const int abase = po - zp - pitch - 1;  // the window of the first neighbour row
       if (mat == 0)
-        res_apply<0, TN>(R, s_p, abase, pitch, zp, cstride, acc);
+        res_apply<0, TN, SPARSE>(R, s_p, abase, pitch, zp, cstride, acc);
       else if (mat == 1)
-        res_apply<1, TN>(R, s_p, abase, pitch, zp, cstride, acc);
+        res_apply<1, TN, SPARSE>(R, s_p, abase, pitch, zp, cstride, acc);
       else
-        res_apply<2, TN>(R, s_p, abase, pitch, zp, cstride, acc);
+        res_apply<2, TN, SPARSE>(R, s_p, abase, pitch, zp, cstride, acc);
     }
-    if (nfix > 0 && !(dbg & 1)) {  // CTA-uniform
-      unsigned gm = gmask;
-      while (gm) {  // warp-uniform
-        const int e = (__ffs(gm) - 1) * 32 + (tid & 31);
-        gm &= gm - 1;
-        const bool on = e < nfix;
-        const int4 fe = on ? s_fixe[e] : make_int4(0, 0, 0, 0);
-        const int no = ((fe.x >> 8) & 0xff) * zp + (fe.x & 0xff) * pitch + (fe.x >> 16);
-        double y[3];
-        res_fix_group(DT, s_p, no, pitch, zp, cstride, (unsigned)fe.y, on, y);
-        if (on) {
-          s_fixout[e * 3] = y[0];
-          s_fixout[e * 3 + 1] = y[1];
-          s_fixout[e * 3 + 2] = y[2];
-        }
-      }
+    lap(1);
+    if (dofix) {
       __syncthreads();
+      lap(2);
       if (fixmask) {
         int fi = fixbase;
 #pragma unroll
         for (int t = 0; t < TN; ++t)
           if ((fixmask >> t) & 1) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) acc[t][d] += s_fixout[fi * 3 + d];
+            for (int d = 0; d < 3; ++d) acc[t][d] += s_fixout[fi * 3 + d] + s_fixout[(G.fixcap + fi) * 3 + d];
             ++fi;
           }
       }
@@ -762,14 +938,17 @@ __global__ void __launch_bounds__(MAXT, 1)
     s0 = th.p_dot(acc);
     s1 = 0.0;
     cluster_sum2(s0, s1, s_wp, s_redA, G.cs, rank, dbg);
+    lap(3);
     pAp = s0;
     alpha = rz / pAp;
     // ---- r -= alpha Ap, z = k r, z.z, r.z (src/ell.cpp:103-110) ----
-    if (fixmask)
+    if (wfix)
       th.template update<true>(acc, alpha, s0, s1);
     else
       th.template update<false>(acc, alpha, s0, s1);
+    lap(4);
     cluster_sum2(s0, s1, s_wp, s_redB, G.cs, rank, dbg);
+    lap(5);
     pn = sqrt(s0);
     beta = s1 / rz;
     rz = s1;
@@ -781,7 +960,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (!(dbg & 16)) {
       if (!active)
         th.du_update(alpha);
-      else if (fixmask)
+      else if (wfix)
         th.template p_update<true>(alpha, beta);
       else
         th.template p_update<false>(alpha, beta);
@@ -791,8 +970,14 @@ __global__ void __launch_bounds__(MAXT, 1)
         __syncthreads();
         res_push_rows(s_p, s_task, ntask, P.nix, cstride, G.nwarps);
       }
+      lap(6);
       cluster_sync_dbg(dbg);  // every halo row has arrived before the next operator
+      lap(7);
     }
+  }
+  if (timing && (tid & 31) == 0) {
+    long long *o = reinterpret_cast<long long *>(T.partial + (size_t)slot * NRED * T.nblk_max) + ((size_t)rank * 16 + (tid >> 5)) * 8;
+    for (int k = 0; k < 8; ++k) o[k] = s_time[k];
   }
 
   // ---- du back to the pool: own rows, and zeros on the boundary nodes of the ring (no other writer) ----
@@ -830,17 +1015,40 @@ __global__ void __launch_bounds__(MAXT, 1)
 
 typedef void (*res_kernel_t)(const MeshConst, const Lst, int, SlotTables, VecPool, const ResGeom, const PureRows,
                              const ResDtab, int);
-res_kernel_t res_kernel(int tn, int nthreads) {
+template <bool SPARSE>
+res_kernel_t res_kernel_of(int tn, int nthreads) {
   if (nthreads <= 384) switch (tn) {
-      case 6: return k_cg_resident<6, 384>;
-      case 7: return k_cg_resident<7, 384>;
-      default: return k_cg_resident<8, 384>;
+      case 6: return k_cg_resident<6, 384, SPARSE>;
+      case 7: return k_cg_resident<7, 384, SPARSE>;
+      default: return k_cg_resident<8, 384, SPARSE>;
     }
   switch (tn) {
-    case 6: return k_cg_resident<6, 512>;
-    case 7: return k_cg_resident<7, 512>;
-    default: return k_cg_resident<8, 512>;
+    case 6: return k_cg_resident<6, 512, SPARSE>;
+    case 7: return k_cg_resident<7, 512, SPARSE>;
+    default: return k_cg_resident<8, 512, SPARSE>;
   }
+}
+res_kernel_t res_kernel(int tn, int nthreads, bool sparse) {
+  return sparse ? res_kernel_of<true>(tn, nthreads) : res_kernel_of<false>(tn, nthreads);
+}
+
+// true when every entry of the three pure-material row blocks that the mirror symmetry of an axis-aligned orthotropic
+// material makes vanish (components fi != fj towards a neighbour whose offset along fi or fj is zero) is zero up to
+// rounding (1e-13 of the block's largest entry): the SPARSE operator copy then skips those 90 of 243 entries
+bool res_rows_sparse(const PureRows &R) {
+  for (int m = 0; m < 3; ++m) {
+    double amax = 0.0;
+    for (int q = 0; q < RB_LEN; ++q) amax = std::max(amax, fabs(R.a[m * RB_LEN + q]));
+    for (int nbr = 0; nbr < 27; ++nbr) {
+      const int o[3] = {nbr % 3 - 1, (nbr / 3) % 3 - 1, nbr / 9 - 1};
+      for (int fi = 0; fi < 3; ++fi)
+        for (int fj = 0; fj < 3; ++fj)
+          if (fi != fj && !(o[fi] != 0 && o[fj] != 0) &&
+              fabs(R.a[m * RB_LEN + nbr * RB_NBR + fi * 3 + fj]) > 1e-13 * amax)
+            return false;
+    }
+  }
+  return true;
 }
 
 template <class T>
@@ -857,8 +1065,10 @@ struct mgpu_int::ResState {
   ResGeom g;
   int4 *d_tinfo = nullptr, *d_fixe = nullptr;
   int2 *d_task = nullptr;
+  unsigned *d_wpiece = nullptr;
   ResDtab dtab;
   int max_clusters = 0;
+  bool sparse = false;  // the pure-material row blocks have the mirror-symmetry zero pattern (res_rows_sparse)
   int dbg = 0;  // MICROPP_RES_DBG: timing experiments only (tools/resident_phases.py) -- results are wrong with any bit set
 };
 
@@ -884,6 +1094,9 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
   rs->d_tinfo = res_to_device(c, plan.tinfo);
   rs->d_fixe = res_to_device(c, plan.fixe);
   rs->d_task = res_to_device(c, plan.task);
+  if (plan.wpiece.empty()) plan.wpiece.assign((size_t)plan.g.cs * 16, 0u);
+  rs->d_wpiece = res_to_device(c, plan.wpiece);
+  rs->g.wpiece = rs->d_wpiece;
   rs->g.tinfo = rs->d_tinfo;
   rs->g.fixe = rs->d_fixe;
   rs->g.task = rs->d_task;
@@ -893,7 +1106,10 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
       for (int q = 0; q < RES_DLEN; ++q) rs->dtab.d[a + b - 1][q] = res_dtab_entry(cfg->ke_elastic, a, b, q);
   CK(cudaStreamSynchronize(c->stream));  // k_rows_build has filled rkinv: ids 0..2 are the pure-material row blocks
   CK(cudaMemcpy(&rs->g.rkp[0][0], c->V.rkinv, sizeof(double) * 9, cudaMemcpyDeviceToHost));
-  res_kernel_t kern = res_kernel(rs->g.tn, rs->g.nthreads);
+  rs->sparse = res_rows_sparse(c->pure_rows);
+  if (const char *env = getenv("MICROPP_RESIDENT_DENSE"))
+    if (atoi(env) != 0) rs->sparse = false;
+  res_kernel_t kern = res_kernel(rs->g.tn, rs->g.nthreads, rs->sparse);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rs->g.smem_bytes));
   cudaLaunchConfig_t cfgl = {};
   cfgl.gridDim = dim3(rs->g.cs, 1, 1);
@@ -915,6 +1131,7 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
     cudaFree(rs->d_tinfo);
     cudaFree(rs->d_fixe);
     cudaFree(rs->d_task);
+    cudaFree(rs->d_wpiece);
     delete rs;
     return;
   }
@@ -923,8 +1140,8 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
   c->res = rs;
   if (verbose)
     fprintf(stderr, "micropp-b200: cluster-resident DPCG: %d CTAs (%d x %d) x %d threads, %d nodes per thread, %d B of "
-                    "shared memory, %d clusters in flight\n", rs->g.cs, rs->g.py, rs->g.pz, rs->g.nthreads, rs->g.tn,
-            rs->g.smem_bytes, ncl);
+                    "shared memory, %d clusters in flight, %s operator\n", rs->g.cs, rs->g.py, rs->g.pz, rs->g.nthreads,
+            rs->g.tn, rs->g.smem_bytes, ncl, rs->sparse ? "153-term (mirror-symmetric row blocks)" : "243-term");
 }
 
 void mgpu_int::resident_destroy(mgpu_ctx *c) {
@@ -932,6 +1149,7 @@ void mgpu_int::resident_destroy(mgpu_ctx *c) {
   cudaFree(c->res->d_tinfo);
   cudaFree(c->res->d_fixe);
   cudaFree(c->res->d_task);
+  cudaFree(c->res->d_wpiece);
   delete c->res;
   c->res = nullptr;
 }
@@ -950,7 +1168,7 @@ void mgpu_int::launch_cg_resident(mgpu_ctx *c, int l, int n) {
   at[0].val.clusterDim.z = 1;
   cfgl.attrs = at;
   cfgl.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfgl, res_kernel(rs->g.tn, rs->g.nthreads), c->mc, lst_of(c, l), n, c->T, c->V, rs->g, c->pure_rows,
+  CK(cudaLaunchKernelEx(&cfgl, res_kernel(rs->g.tn, rs->g.nthreads, rs->sparse), c->mc, lst_of(c, l), n, c->T, c->V, rs->g, c->pure_rows,
                         rs->dtab, rs->dbg));
 }
 
@@ -1012,6 +1230,18 @@ float mgpu_bench_resident(mgpu_ctx *c, int n, int reps, int dbg) {
   return ms / reps;
 }
 
+// dbg bit 256: the per-warp phase counters the kernel left for `slot` ([8 ranks][16 warps][8 phases] cycles)
+void mgpu_resident_timeline(mgpu_ctx *c, int slot, long long *out1024) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if ((size_t)NRED * c->T.nblk_max < 1024) {
+    memset(out1024, 0, 1024 * sizeof(long long));
+    return;
+  }
+  CK(cudaMemcpy(out1024, c->T.partial + (size_t)slot * NRED * c->T.nblk_max, 1024 * sizeof(long long),
+                cudaMemcpyDeviceToHost));
+}
+
 // Host-only replay of the plan (tests/test_resident_plan.py, no GPU): applies the operator to p exactly as the kernel
 // does -- per CTA a zeroed brick, own rows stored, halo rows delivered by res_push_dests, the chunk's pure-material row
 // block on every node of a chunk and res_fix_corr on the interface entries -- and returns Ap.  p / Ap: [3][nn]
@@ -1042,17 +1272,16 @@ int mgpu_resident_replay_host(int nx, int ny, int nz, const int *elem_type, cons
   for (int a = 0; a < 3; ++a)
     for (int b = a + 1; b < 3; ++b)
       for (int q = 0; q < RES_DLEN; ++q) D[(size_t)(a + b - 1) * RES_DLEN + q] = res_dtab_entry(ke, a, b, q);
-  // every group of 32 interface entries belongs to exactly one warp of its CTA
+  // every interface piece (group of 32 entries x half of the element positions) belongs to exactly one warp of its CTA
   for (int r = 0; r < G.cs; ++r) {
-    int seen = 0;
-    for (int w = 0; w < G.nwarps; ++w) {
-      const int gm = (int)((unsigned)plan.tinfo[(size_t)r * G.nthreads + w * 32].w >> 16);
-      for (int l = 1; l < 32; ++l)
-        if ((int)((unsigned)plan.tinfo[(size_t)r * G.nthreads + w * 32 + l].w >> 16) != gm) return -4;
-      if (seen & gm) return -4;
-      seen |= gm;
+    unsigned seen = 0;
+    for (int w = 0; w < 16; ++w) {
+      const unsigned pm = plan.wpiece.empty() ? 0u : plan.wpiece[(size_t)r * 16 + w];
+      if ((seen & pm) || (pm && w >= G.nwarps)) return -4;
+      seen |= pm;
     }
-    if (seen != (1 << ((G.nfix[r] + 31) / 32)) - 1) return -4;
+    const int npc = 2 * ((G.nfix[r] + RES_GROUP - 1) / RES_GROUP);
+    if (seen != (npc >= 32 ? 0xffffffffu : (1u << npc) - 1u)) return -4;
   }
   std::vector<std::vector<double>> brick(G.cs, std::vector<double>((size_t)3 * G.cstride, 0.0));
   // own values, then the push tasks (row copies between the bricks)
@@ -1102,7 +1331,10 @@ int mgpu_resident_replay_host(int nx, int ny, int nz, const int *elem_type, cons
           }
         }
         if ((fixmask >> t) & 1) {
-          const int4 fe = plan.fixe[(size_t)r * G.fixcap + fi];
+          int4 fe = make_int4(0, 0, 0, -1);
+          for (int q = 0; q < G.nfix[r]; ++q)  // the list is in work order: look the owner index up
+            if (plan.fixe[(size_t)r * G.fixcap + q].w == fi) fe = plan.fixe[(size_t)r * G.fixcap + q];
+          if (fe.w != fi) return -5;
           const int no = ((fe.x >> 8) & 0xff) * G.zp + (fe.x & 0xff) * G.pitch + (fe.x >> 16);
           if (no != lz * G.zp + ly * G.pitch + i0 + t) return -2;
           double cr[3];

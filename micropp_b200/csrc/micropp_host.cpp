@@ -1064,6 +1064,9 @@ double micropp3x_apply_operator(micropp3 *s, const double *p, double *Ap, int op
 double micropp3x_bench_spmv(micropp3 *s, int nslots, int iters) {
   return mgpu_bench_spmv(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, iters);
 }
+void micropp3x_resident_timeline(micropp3 *s, int slot, long long *out1024) {
+  mgpu_resident_timeline(mpp_access::engine((micropp<3> *)s->ptr)->ctx, slot, out1024);
+}
 double micropp3x_bench_resident(micropp3 *s, int nslots, int reps, int dbg) {
   return mgpu_bench_resident(mpp_access::engine((micropp<3> *)s->ptr)->ctx, nslots, reps, dbg);
 }
