@@ -50,9 +50,10 @@ struct ResGeom {
   int nthreads, nwarps;
   int fixcap;          // interface-node entries per CTA (max over the ranks)
   int ntask[RES_MAX_CS], taskcap;  // halo rows to push after every p update
+  int halo_in[RES_MAX_CS];         // bytes of halo rows a CTA receives per p update (transaction count of its mbarrier)
   int y0[RES_MAX_CS], y1[RES_MAX_CS], z0[RES_MAX_CS], z1[RES_MAX_CS];  // owned INTERIOR (0-based) row ranges
   int nfix[RES_MAX_CS];
-  int off_du, off_r2, off_task, off_time, off_fixe, off_fixk, off_fixout, off_red, off_wp, smem_bytes;
+  int off_du, off_r2, off_task, off_time, off_mbar, off_fixe, off_fixk, off_fixout, off_red, off_wp, smem_bytes;
   double rkp[3][3];    // 1 / diagonal of the three pure-material row blocks (the Jacobi preconditioner of most nodes)
   const int4 *tinfo;   // [cs][nthreads]  x: ly | lz << 8 | chunk << 16 | material << 24 (-1: idle thread)
                        //                 y: valid-node mask | interface-node mask << 8, z: first interface entry,
@@ -360,6 +361,7 @@ bool res_plan_try(int nx, int ny, int nz, const int *elem_type, const int *rowid
       }
     G.ntask[r] = (int)task[r].size();
     G.taskcap = std::max(G.taskcap, G.ntask[r]);
+    for (const int2 &tk : task[r]) G.halo_in[(unsigned)tk.y >> 24] += 3 * nix * (int)sizeof(double);
   }
   if (3 * G.cstride >= (1 << 24)) return false;
   out.task.assign((size_t)cs * std::max(G.taskcap, 1), make_int2(0, 0));
@@ -375,6 +377,8 @@ bool res_plan_try(int nx, int ny, int nz, const int *elem_type, const int *rowid
   if (G.nthreads > 384) off += up(sizeof(double) * G.dstride);
   G.off_task = (int)off;
   off += up(sizeof(int2) * G.taskcap);
+  G.off_mbar = (int)off;
+  off += up(sizeof(uint64_t) * 4);  // mbarriers: dot products A, dot products B, halo rows
   G.off_time = (int)off;
   off += up(sizeof(long long) * 16 * 9);  // phase counters of the timeline instrument (dbg bit 256)
   G.off_fixe = (int)off;
@@ -453,10 +457,24 @@ __device__ __forceinline__ void st_cluster_f64(unsigned addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
 }
 
+// Asynchronous store into the shared memory of another CTA of the cluster that signals the DESTINATION's mbarrier with its
+// byte count (st.async ... mbarrier::complete_tx): the receiver waits on its own mbarrier -- no cluster barrier, no
+// cluster-scope fence (which ptxas turns into MEMBAR.ALL.GPU + an L1 invalidation) anywhere in the DPCG loop.
+__device__ __forceinline__ void st_async_f64(unsigned addr, double v, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(addr), "d"(v),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2f64(unsigned addr, double a, double b, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];\n" ::"r"(addr),
+               "d"(a), "d"(b), "r"(mbar)
+               : "memory");
+}
+
 // Sums a and b over every thread of the cluster; the same bits in every thread of every CTA.  s_wp: [2][16] per-warp
 // partials (unused entries stay zero), s_red: [RES_MAX_CS][2] per-CTA sums (entries of absent ranks stay zero).
-__device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp, double *s_red, int cs, unsigned rank,
-                                             int dbg) {
+__device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp, double *s_red, uint64_t *mbar,
+                                             unsigned &parity, int cs, unsigned rank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   a = warp_sum(a);
   b = warp_sum(b);
@@ -465,6 +483,7 @@ __device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp,
     s_wp[16 + w] = b;
   }
   __syncthreads();
+  if (threadIdx.x == 0) mbar_expect_tx(mbar, 16u * (unsigned)cs);  // this phase: one arrival + 16 B from every CTA
   if ((int)threadIdx.x < cs) {  // thread q delivers this CTA's sums to CTA q
     double sa = 0.0, sb = 0.0;
 #pragma unroll
@@ -472,11 +491,10 @@ __device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp,
       sa += s_wp[ww];
       sb += s_wp[16 + ww];
     }
-    const unsigned ra = map_to_rank(&s_red[2 * rank], threadIdx.x);
-    st_cluster_f64(ra, sa);
-    st_cluster_f64(ra + 8, sb);
+    st_async_v2f64(map_to_rank(&s_red[2 * rank], threadIdx.x), sa, sb, map_to_rank(mbar, threadIdx.x));
   }
-  cluster_sync_dbg(dbg);
+  mbar_wait(mbar, parity);
+  parity ^= 1u;
   a = 0.0;
   b = 0.0;
 #pragma unroll
@@ -623,14 +641,16 @@ __device__ __forceinline__ void res_fix_piece(const ResDtab &DT, const double *_
 // the halo copies of the own rows: warp per (row, neighbour) task, lanes along x -- coalesced remote stores through
 // distributed shared memory
 __device__ __forceinline__ void res_push_rows(const double *s_p, const int2 *s_task, int ntask, int nix, int cstride,
-                                              int nwarps) {
+                                              int nwarps, uint64_t *mbar) {
   const int lane = threadIdx.x & 31;
   for (int k = threadIdx.x >> 5; k < ntask; k += nwarps) {
     const int2 tk = s_task[k];
-    const unsigned base = map_to_rank(s_p + (tk.y & 0xffffff), (unsigned)tk.y >> 24);
+    const unsigned dr = (unsigned)tk.y >> 24;
+    const unsigned base = map_to_rank(s_p + (tk.y & 0xffffff), dr), rmb = map_to_rank(mbar, dr);
     for (int x = lane; x < nix; x += 32) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) st_cluster_f64(base + (unsigned)((d * cstride + x) * 8), s_p[tk.x + d * cstride + x]);
+      for (int d = 0; d < 3; ++d)
+        st_async_f64(base + (unsigned)((d * cstride + x) * 8), s_p[tk.x + d * cstride + x], rmb);
     }
   }
 }
@@ -777,6 +797,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   double *s_redA = reinterpret_cast<double *>(s_raw + G.off_red);
   double *s_redB = s_redA + 2 * RES_MAX_CS;
   double *s_wp = reinterpret_cast<double *>(s_raw + G.off_wp);
+  uint64_t *s_mbar = reinterpret_cast<uint64_t *>(s_raw + G.off_mbar);  // [0] dot products A, [1] B, [2] halo rows
 
   const int tid = threadIdx.x;
   const unsigned rank = cluster_ctarank();
@@ -788,10 +809,18 @@ __global__ void __launch_bounds__(MAXT, 1)
   const size_t vo = (size_t)slot * V.vstride;
   const int pitch = G.pitch, nyb = G.nyb, zp = G.zp, cstride = G.cstride;
   const int nfix = G.nfix[rank], ntask = (dbg & 2) ? 0 : G.ntask[rank];
+  const unsigned halo_in = (dbg & 2) ? 0u : (unsigned)G.halo_in[rank];
+  unsigned parA = 0, parB = 0, parC = 0;
 
   // ---- set-up: zero brick, du and the reduction mailboxes; tables into shared memory ----
   for (int q = tid; q < 3 * cstride; q += blockDim.x) s_p[q] = 0.0;
   for (int q = tid; q < 3 * G.dstride; q += blockDim.x) s_du[q] = 0.0;
+  if (tid == 0) {
+    mbar_init(&s_mbar[0], 1);
+    mbar_init(&s_mbar[1], 1);
+    mbar_init(&s_mbar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   if (tid < 4 * RES_MAX_CS) s_redA[tid] = 0.0;
   if (tid < 32) s_wp[tid] = 0.0;
   for (int q = tid; q < G.ntask[rank]; q += blockDim.x) s_task[q] = __ldg(&G.task[(size_t)rank * G.taskcap + q]);
@@ -851,11 +880,21 @@ __global__ void __launch_bounds__(MAXT, 1)
     else
       th.template init<false>(bv, s0, s1);
   }
-  if (ntask > 0) {  // CTA-uniform
-    __syncthreads();
-    res_push_rows(s_p, s_task, ntask, P.nix, cstride, G.nwarps);
-  }
-  cluster_sum2(s0, s1, s_wp, s_redB, G.cs, rank, dbg);  // also orders the pushes before the first operator
+  // halo rows: pushed into the neighbours' bricks with their byte count signalled on the neighbours' mbarrier [2]; a
+  // CTA starts the operator when its own mbarrier says that all its halo bytes have landed.  No hazard on the bricks:
+  // a CTA pushes the rows of iteration i + 1 only after the dot products of iteration i, i.e. after every CTA of the
+  // cluster has finished reading the halo of iteration i.
+  auto halo_exchange = [&]() {
+    __syncthreads();  // the new p of the own rows is complete (the operator reads the rows of other threads)
+    if (tid == 0 && halo_in > 0) mbar_expect_tx(&s_mbar[2], halo_in);
+    if (ntask > 0) res_push_rows(s_p, s_task, ntask, P.nix, cstride, G.nwarps, &s_mbar[2]);
+    if (halo_in > 0) {  // CTA-uniform
+      mbar_wait(&s_mbar[2], parC);
+      parC ^= 1u;
+    }
+  };
+  halo_exchange();
+  cluster_sum2(s0, s1, s_wp, s_redB, &s_mbar[1], parB, G.cs, rank);
   double rz = s0, pn = sqrt(s1), alpha = 0.0, beta = 0.0, pAp = 0.0;
   const double pnorm0 = pn;
   int its = 0;
@@ -937,7 +976,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     // ---- p.Ap, alpha (src/ell.cpp:97-100) ----
     s0 = th.p_dot(acc);
     s1 = 0.0;
-    cluster_sum2(s0, s1, s_wp, s_redA, G.cs, rank, dbg);
+    cluster_sum2(s0, s1, s_wp, s_redA, &s_mbar[0], parA, G.cs, rank);
     lap(3);
     pAp = s0;
     alpha = rz / pAp;
@@ -947,7 +986,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     else
       th.template update<false>(acc, alpha, s0, s1);
     lap(4);
-    cluster_sum2(s0, s1, s_wp, s_redB, G.cs, rank, dbg);
+    cluster_sum2(s0, s1, s_wp, s_redB, &s_mbar[1], parB, G.cs, rank);
     lap(5);
     pn = sqrt(s0);
     beta = s1 / rz;
@@ -966,12 +1005,8 @@ __global__ void __launch_bounds__(MAXT, 1)
         th.template p_update<false>(alpha, beta);
     }
     if (active) {
-      if (ntask > 0) {  // CTA-uniform
-        __syncthreads();
-        res_push_rows(s_p, s_task, ntask, P.nix, cstride, G.nwarps);
-      }
       lap(6);
-      cluster_sync_dbg(dbg);  // every halo row has arrived before the next operator
+      halo_exchange();  // every halo row has arrived before the next operator
       lap(7);
     }
   }
