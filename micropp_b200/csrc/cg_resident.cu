@@ -437,26 +437,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void cluster_sync_relaxed() {
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void cluster_sync_dbg(int dbg) {
-  if (dbg & 32)
-    cluster_sync_relaxed();
-  else
-    cluster_sync_all();
-}
 // shared::cluster address of the same variable in CTA `rank` of the cluster
 __device__ __forceinline__ unsigned map_to_rank(const void *local_smem, unsigned rank) {
   unsigned la = (unsigned)__cvta_generic_to_shared(local_smem), ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(la), "r"(rank));
   return ra;
 }
-__device__ __forceinline__ void st_cluster_f64(unsigned addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
-}
-
 // Asynchronous store into the shared memory of another CTA of the cluster that signals the DESTINATION's mbarrier with its
 // byte count (st.async ... mbarrier::complete_tx): the receiver waits on its own mbarrier -- no cluster barrier, no
 // cluster-scope fence (which ptxas turns into MEMBAR.ALL.GPU + an L1 invalidation) anywhere in the DPCG loop.

@@ -392,6 +392,7 @@ struct mgpu_ctx {
   int ngp = 0, W = 0;
   bool all_elastic = true;
   bool implicit = false;  // all-elastic RVE served by the implicit operator (no per-slot matrices)
+  bool rhs_operator = false;  // all-elastic RVE: assembly_rhs as b = -A u through the implicit operator
   bool hybrid = false;    // RVE with a damage / plastic phase: implicit tables built too, OP_HYBRID available
   int hyb_max = 0;        // a slot takes the hybrid operator while its node list holds at most this many rows
   bool defer_fold = false;  // launch_imp_spmv leaves the p.Ap fold to the caller (hybrid SpMV adds its correction first)

@@ -190,6 +190,51 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
+// assembly_rhs of an ALL-ELASTIC RVE through the implicit operator: every material is linear, so the internal force is
+// K u and the interior rows of -b are the ELL row blocks applied to u WITH its boundary values (the row block of an
+// interior node holds the coupling to its boundary neighbours; the Dirichlet rows themselves are identity rows and b
+// vanishes there, src/assembly.cpp:61-104).  u is copied into the operator's input vector, the implicit SpMV runs once
+// (243 FMA and 48 B per node instead of 8 Gauss-point stress evaluations per element and a 192 B per element scratch
+// round trip), and b = -A u with ||b||^2 and the Newton loop-head logic follows.  Same mathematics as the element loop
+// of k_elem_rhs + k_asm_rhs, other rounding (1e-15 of |K||u|).
+__global__ void __launch_bounds__(NT)
+    k_u_to_p(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int mode) {
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  if (mode == 1 && !T.state[slot].nr_active) return;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= P.nn) return;
+  const size_t vo = (size_t)slot * V.vstride;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) V.p[vo + (size_t)d * P.nn_pad + n] = V.u[vo + (size_t)d * P.nn_pad + n];
+}
+__global__ void __launch_bounds__(NT)
+    k_rhs_from_ap(const __grid_constant__ MeshConst P, const Lst L, SlotTables T, VecPool V, int mode) {
+  __shared__ double sm[NRED * (NT / 32)];
+  __shared__ int sflag;
+  const int slot = slot_of(L);
+  if (slot < 0) return;
+  mgpu_slot_state *st = &T.state[slot];
+  if (mode == 1 && !st->nr_active) return;
+  const size_t vo = (size_t)slot * V.vstride;
+  const int n = blockIdx.x * NT + threadIdx.x;
+  double nrm[1] = {0.0};
+  if (n < P.nn) {
+    int i, j, k;
+    node_ijk(P, n, i, j, k);
+    const bool bnd = on_boundary(P, i, j, k);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const size_t ix = vo + (size_t)d * P.nn_pad + n;
+      const double bv = bnd ? 0.0 : -V.Ap[ix];
+      V.b[ix] = bv;
+      nrm[0] += bv * bv;
+    }
+  }
+  double *partial = T.partial + (size_t)slot * NRED * T.nblk_max;
+  if (grid_sum<1>(nrm, partial, T.nblk_max, &st->ticket, sm, &sflag) && threadIdx.x == 0) tail_rhs(P, st, nrm[0], mode);
+}
+
 // ------------------------------------------------------------------------------------------------
 // assembly_mat, all-elastic RVE (src/assembly.cpp:106-178 + src/ell-common.cpp:166-297).
 // Element matrices of elastic materials do not depend on u (src/material.cpp:84-94), so each node
@@ -1735,6 +1780,10 @@ mgpu_ctx *mgpu_create(const mgpu_config *cfg) {
     implicit_setup(c, cfg, &nblk_max);
     if (c->hybrid && c->imp_kernel != IMP_TMAC) c->hybrid = false;
   }
+  // all-elastic RVEs evaluate the residual through the implicit operator (k_u_to_p); MICROPP_RHS_OPERATOR=0 keeps the
+  // element loop (k_elem_rhs + k_asm_rhs), which every RVE with a damage / plastic phase and every z-slab uses
+  c->rhs_operator = c->implicit && !P.slab;
+  if (const char *env = getenv("MICROPP_RHS_OPERATOR")) c->rhs_operator = c->rhs_operator && atoi(env) != 0;
 
   SlotTables &T = c->T;
   T.nblk_max = nblk_max;
@@ -1976,6 +2025,14 @@ void mgpu_set_bc(mgpu_ctx *c, int l, int n) {
 void mgpu_asm_rhs(mgpu_ctx *c, int l, int n, int mode) {
   if (n <= 0) return;
   ProfScope ps(c, 2, n);
+  if (c->rhs_operator) {  // all-elastic RVE: b = -A u through the implicit operator (k_u_to_p above)
+    k_u_to_p<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, mode);
+    launch_imp_spmv(c, l, n, 1, c->imp_kernel);
+    k_rhs_from_ap<<<node_grid(c, n), NT, 0, c->stream>>>(c->mc, lst_of(c, l), c->T, c->V, mode);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    return;
+  }
   const size_t bstride = (size_t)24 * c->mc.nelem_pad;
   for (int off = 0; off < n; off += c->be_chunk) {
     const int cnt = std::min(c->be_chunk, n - off);

@@ -16,13 +16,16 @@ def run(mod_cls, params, eps, implicit=None, kernel=None):
     (MICROPP_IMPLICIT: 0 = one assembled ELL matrix per slot; MICROPP_IMP_KERNEL: 0 = k_spmv_dot_imp, the table-driven
     multi-RHS kernel, 3 = k_spmv_dot_tmac + k_spmv_fix (TMA load and TMA store) when nx is even -- both inside the
     three-kernel DPCG loop (MICROPP_RESIDENT=0); unset = the default: the cluster-resident DPCG kernel whenever the RVE
-    fits a cluster, tests/test_gpu_resident.py)."""
+    fits a cluster, tests/test_gpu_resident.py).  The residual of an all-elastic RVE is b = -A u through the implicit
+    operator by default; kernel 0 keeps the element loop (MICROPP_RHS_OPERATOR=0) for the bit-wise comparison."""
     env = {}
     if implicit is not None:
         env["MICROPP_IMPLICIT"] = "1" if implicit else "0"
     if kernel is not None:
         env["MICROPP_IMP_KERNEL"] = str(kernel)
         env["MICROPP_RESIDENT"] = "0"
+    if kernel == 0:
+        env["MICROPP_RHS_OPERATOR"] = "0"   # the element loop of assembly_rhs, as the explicit path (bit-wise comparison)
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:

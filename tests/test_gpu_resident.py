@@ -165,3 +165,25 @@ def test_residual_history_against_three_kernel_loop(mpp):
     assert abs(len(a) - len(b)) <= 1 and n > 10
     assert relerr(a[:12], b[:12]) < 1e-12
     assert np.all(np.abs(a[:n] - b[:n]) <= 1e-6 * np.abs(b[:n]) + 1e-9 * b[0])
+
+
+@pytest.mark.parametrize("dims,kind", [((12, 12, 12), "sphere"), ((9, 11, 10), "fibres3"), ((14, 9, 8), "layers"),
+                                       ((30, 30, 30), "sphere"), ((13, 7, 6), "sphere")])
+def test_residual_through_the_operator(mpp, refpy, dims, kind):
+    """assembly_rhs of an all-elastic RVE as b = -A u through the implicit operator (k_u_to_p, the implicit SpMV,
+    k_rhs_from_ap) against the element loop of the same library (MICROPP_RHS_OPERATOR=0: k_elem_rhs + k_asm_rhs) and
+    against the reference's assembly_rhs (src/assembly.cpp:61-104), for a random u WITH boundary values."""
+    kw = dict(size=dims, ngp=1, lin_stress=False, calc_ctan_lin=False, **ELASTIC[kind])
+    g = mpp.Micropp3(mpp.default_params(**kw))
+    os.environ["MICROPP_RHS_OPERATOR"] = "0"
+    try:
+        ge = mpp.Micropp3(mpp.default_params(**kw))
+    finally:
+        del os.environ["MICROPP_RHS_OPERATOR"]
+    r = refpy.RefMicropp(refpy.default_params(**kw))
+    u = np.random.default_rng(11).uniform(-1e-3, 1e-3, g.nndim)
+    bo, no = g.assembly_rhs(u)
+    be, ne = ge.assembly_rhs(u)
+    br, nr = r.assembly_rhs(u)
+    assert relerr(bo, br) < 1e-12 and relerr(be, br) < 1e-12 and relerr(bo, be) < 1e-12
+    assert abs(no - nr) <= 1e-12 * nr and abs(ne - nr) <= 1e-12 * nr
