@@ -1131,7 +1131,16 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
   if (const char *env = getenv("MICROPP_RESIDENT_DENSE"))
     if (atoi(env) != 0) rs->sparse = false;
   res_kernel_t kern = res_kernel(rs->g.tn, rs->g.nthreads, rs->sparse);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rs->g.smem_bytes));
+  {
+    // the attribute belongs to the kernel, not to this context: only ever raise it (another live context may run the
+    // same instantiation with a larger plan)
+    static std::map<const void *, int> granted;
+    int &have = granted[(const void *)kern];
+    if (rs->g.smem_bytes > have) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rs->g.smem_bytes));
+      have = rs->g.smem_bytes;
+    }
+  }
   cudaLaunchConfig_t cfgl = {};
   cfgl.gridDim = dim3(rs->g.cs, 1, 1);
   cfgl.blockDim = dim3(rs->g.nthreads, 1, 1);

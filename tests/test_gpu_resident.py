@@ -187,3 +187,21 @@ def test_residual_through_the_operator(mpp, refpy, dims, kind):
     br, nr = r.assembly_rhs(u)
     assert relerr(bo, br) < 1e-12 and relerr(be, br) < 1e-12 and relerr(bo, be) < 1e-12
     assert abs(no - nr) <= 1e-12 * nr and abs(ne - nr) <= 1e-12 * nr
+
+
+def test_two_live_contexts_share_a_kernel_instantiation(mpp):
+    """Two live objects whose plans use the same kernel instantiation with different shared-memory sizes: the
+    per-kernel dynamic shared memory attribute must only ever grow (the larger plan is solved after the smaller object
+    was constructed)."""
+    rng = np.random.default_rng(2)
+    big = mpp.Micropp3(params_of(mpp, (14, 14, 14), 2, "sphere"))
+    small = mpp.Micropp3(params_of(mpp, (12, 12, 12), 2, "sphere"))
+    ib, is_ = big.resident_info(), small.resident_info()
+    assert ib and is_ and ib["tn"] == is_["tn"] and (ib["threads"] <= 384) == (is_["threads"] <= 384)
+    assert ib["smem"] > is_["smem"]
+    for obj in (big, small, big):
+        eps = rng.uniform(-1e-3, 1e-3, (2, 6))
+        for gp in range(2):
+            obj.set_strain(gp, eps[gp])
+        obj.homogenize()
+        assert all(obj.has_converged(gp) for gp in range(2))
