@@ -3,23 +3,31 @@
 //
 // The interior (y, z) rows of the RVE are split py x pz over the CTAs of a cluster (<= 8).  A CTA keeps, for the whole
 // solve,
-//   p    its rows plus a one-row halo ring, in shared memory (the "brick": [3 components][(nyl+2)(nzl+2) rows][pitch]);
-//        boundary nodes of the RVE are zeros that are never written (b and x0 vanish there: identity rows)
-//   du   its rows in shared memory,  r  in REGISTERS (a thread owns TN x-adjacent nodes of one row for the whole solve),
+//   p    its rows plus a one-row halo ring, in shared memory (the "brick": [3 components][(nyl+2)(nzl+2) rows + 1][pitch],
+//        odd row pitch + skewed plane pitch: 16 consecutive rows fall into 16 different banks); boundary nodes of the RVE
+//        are zeros that are never written (b and x0 vanish there: identity rows)
+//   du   its rows in shared memory,  r  in REGISTERS (a thread owns TN x-adjacent nodes of one row for the whole solve;
+//        blocks of more than 12 warps keep the third component of r in shared memory),
 //   Ap   only ever exists as the thread's accumulators.
-// Per iteration: the operator (pure-material row block of the chunk as uniform-register DFMA operands, as in
-// k_spmv_dot_tmac; nodes next to a material interface receive the element-wise correction sum_e (Ke_type(e) - Ke_m)
-// p_e from the per-material element matrices in shared memory), three cluster barriers (p.Ap; z.z and r.z; halo), the
-// halo rows of the new p are PUSHED into the neighbour CTAs' bricks through distributed shared memory.  Dot products:
-// warp shuffle -> per-warp partials -> one per-CTA partial pushed into every CTA's mailbox -> every thread adds the
-// per-CTA partials in rank order: identical bits in every CTA (identical loop decisions), identical for every slot.
+// Per iteration:
+//   * the operator: the pure-material row block of the chunk as uniform-register DFMA operands (kernel parameter, as in
+//     k_spmv_dot_tmac), 153 of its 243 terms when the row blocks are mirror-symmetric (res_rows_sparse); nodes next to a
+//     material interface receive the element-wise correction sum_e (Ke_type(e) - Ke_m) p_e from three difference
+//     tables that are a kernel parameter too (res_fix_piece), computed in pieces that level the SM quarters;
+//   * two dot-product reductions (p.Ap; z.z and r.z): warp shuffle -> per-warp partials -> one per-CTA pair sent into the
+//     mailbox of every CTA -> every thread adds the per-CTA partials in rank order: identical bits in every CTA
+//     (identical loop decisions), identical for every slot;
+//   * the halo rows of the new p are PUSHED into the neighbour CTAs' bricks.
+//   Mailboxes and halo rows travel as st.async ... mbarrier::complete_tx through distributed shared memory; a CTA waits
+//   on its OWN mbarriers: there is no cluster barrier and no cluster-scope fence inside the loop.
 // HBM traffic of a solve: b in, du out (48 B per node), instead of 248 B per node and ITERATION of the three-kernel
 // loop.  The scalar logic (alpha, beta, loop-head test, iteration count, residual history) is the reference's, as in
 // tail_cg_init / tail_spmv / tail_cg_update.
 //
-// Availability: all-elastic RVE (implicit operator), not a z-slab, and a decomposition whose brick + du + interface
-// tables fit the 227 KB of one SM (30^3: 8 CTAs of 14 x 7 rows, 214 KB).  Larger RVEs keep the three-kernel loop
-// (k_spmv_dot_tmac + k_cg_update_imp + k_cg_pupdate_imp); said on stderr at context creation when MICROPP_VERBOSE is set.
+// Availability: all-elastic RVE (implicit operator), not a z-slab, and a decomposition whose brick + du + tables fit
+// the 227 KB of one SM (30^3: 8 CTAs of 14 x 7 rows, 222 KB).  Larger RVEs keep the three-kernel loop (k_spmv_dot_tmac +
+// k_cg_update_imp + k_cg_pupdate_imp); said on stderr at context creation when MICROPP_VERBOSE is set.
+// Measurements, the optimisation log and the dead ends: profiles/r04_resident_dpcg.md; DESIGN.md section 5.1b.
 #include "mgpu_internal.cuh"
 
 using namespace mgpu_int;
@@ -57,7 +65,7 @@ struct ResGeom {
   double rkp[3][3];    // 1 / diagonal of the three pure-material row blocks (the Jacobi preconditioner of most nodes)
   const int4 *tinfo;   // [cs][nthreads]  x: ly | lz << 8 | chunk << 16 | material << 24 (-1: idle thread)
                        //                 y: valid-node mask | interface-node mask << 8, z: first interface entry,
-                       //                 w: own row | (interface groups this thread's WARP computes) << 16
+                       //                 w: own row (index into du)
   const int4 *fixe;    // [cs][fixcap]    x: ly | lz << 8 | i << 16, y: 8 codes of 3 bits, one per element position (0: element
                        //                 of the chunk's material m; else (1 + u) | neg << 2 for an element of type t: u the
                        //                 pair {m, t}, neg = t < m, i.e. the correction is -D_u), z: row-block id,
