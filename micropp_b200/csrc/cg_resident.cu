@@ -28,6 +28,8 @@
 // the 227 KB of one SM (30^3: 8 CTAs of 14 x 7 rows, 222 KB).  Larger RVEs keep the three-kernel loop (k_spmv_dot_tmac +
 // k_cg_update_imp + k_cg_pupdate_imp); said on stderr at context creation when MICROPP_VERBOSE is set.
 // Measurements, the optimisation log and the dead ends: profiles/r04_resident_dpcg.md; DESIGN.md section 5.1b.
+#include <mutex>
+
 #include "mgpu_internal.cuh"
 
 using namespace mgpu_int;
@@ -465,6 +467,26 @@ __device__ __forceinline__ void st_async_v2f64(unsigned addr, double a, double b
                : "memory");
 }
 
+// mbarrier wait with a bound: a transaction that never arrives (a bug in the byte accounting, a CTA of the cluster lost)
+// becomes a launch failure with a CUDA error on the host instead of a hung device (2^26 polls of a try_wait that itself
+// waits a hardware time slice: seconds, against microseconds for a DPCG iteration).
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+
 // Sums a and b over every thread of the cluster; the same bits in every thread of every CTA.  s_wp: [2][16] per-warp
 // partials (unused entries stay zero), s_red: [RES_MAX_CS][2] per-CTA sums (entries of absent ranks stay zero).
 __device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp, double *s_red, uint64_t *mbar,
@@ -487,7 +509,7 @@ __device__ __forceinline__ void cluster_sum2(double &a, double &b, double *s_wp,
     }
     st_async_v2f64(map_to_rank(&s_red[2 * rank], threadIdx.x), sa, sb, map_to_rank(mbar, threadIdx.x));
   }
-  mbar_wait(mbar, parity);
+  mbar_wait_bounded(mbar, parity);
   parity ^= 1u;
   a = 0.0;
   b = 0.0;
@@ -883,7 +905,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (tid == 0 && halo_in > 0) mbar_expect_tx(&s_mbar[2], halo_in);
     if (ntask > 0) res_push_rows(s_p, s_task, ntask, P.nix, cstride, G.nwarps, &s_mbar[2]);
     if (halo_in > 0) {  // CTA-uniform
-      mbar_wait(&s_mbar[2], parC);
+      mbar_wait_bounded(&s_mbar[2], parC);
       parC ^= 1u;
     }
   };
@@ -1143,6 +1165,8 @@ void mgpu_int::resident_setup(mgpu_ctx *c, const mgpu_config *cfg, const int *ro
     // the attribute belongs to the kernel, not to this context: only ever raise it (another live context may run the
     // same instantiation with a larger plan)
     static std::map<const void *, int> granted;
+    static std::mutex granted_lock;
+    std::lock_guard<std::mutex> guard(granted_lock);
     int &have = granted[(const void *)kern];
     if (rs->g.smem_bytes > have) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, rs->g.smem_bytes));
