@@ -248,7 +248,7 @@ class Env:
         return self._red(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
 
 
-def resident_roofline(n, info, res_ms, prof, prof_ms, apps, nsteps, ngp):
+def resident_roofline(n, info, res_ms, prof, prof_ms, apps, nsteps, ngp, name="elastic30"):
     """roofline of k_cg_resident: the WHOLE DPCG solve of an all-elastic RVE inside one thread-block cluster (operator,
     dot products, vector updates; p and du in shared memory, r in registers).  Its bound is the FP64 pipe: a DPCG
     iteration moves no HBM byte, a solve reads b and writes du (48 B per node).  `achieved` counts the ALGORITHMIC
@@ -261,14 +261,25 @@ def resident_roofline(n, info, res_ms, prof, prof_ms, apps, nsteps, ngp):
     tf = flops / sec / 1e12
     solves = ngp * nsteps
     hbm_bytes = 48.0 * nn * solves
-    return {"kernel": "k_cg_resident (whole DPCG solve: operator + dot products + vector updates of every iteration in "
+    traffic, traffic_src = None, None
+    tr = ROOT / "profiles" / "spmv_traffic.json"
+    if tr.exists():   # DRAM counters need ncu's kernel replay: the per-solve byte count of the committed capture, scaled
+        try:
+            ent = json.loads(tr.read_text())[name]["resident"]
+            traffic = ent["dram_bytes_per_rve_solve"] * ngp      # one launch = one solve of every RVE of the wave
+            traffic_src = "from profiles/: " + ent["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum per " \
+                          "RVE solve, not measured live)"
+        except Exception:
+            pass
+    r_extra = {"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 48.0 * nn * ngp}
+    return {**r_extra, "kernel": "k_cg_resident (whole DPCG solve: operator + dot products + vector updates of every iteration in "
                       "ONE launch, one thread-block cluster per RVE; no HBM traffic inside the loop)",
             "bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
             "peak_source": "nominal FP64: 148 SM x 64 DFMA/clk x 1965 MHz; a cluster of %d CTAs x %d clusters in flight "
                            "occupies %d of the 148 SMs" % (info["cs"], info["clusters"], info["cs"] * info["clusters"]),
             "flops_counted": "2 x 243 x interior nodes per DPCG iteration (the dense 27 x 3 x 3 stencil of SURVEY 8d); "
                              "the kernel runs the 153 structurally non-zero terms of a mirror-symmetric row block",
-            "traffic": None, "rve_applications": apps, "launches": None, "kernel_ms": res_ms,
+            "rve_applications": apps, "launches": solves / max(ngp, 1), "kernel_ms": res_ms,
             "share_of_step": res_ms / max(prof_ms, 1e-9), "instrumented_step_ms": prof_ms / nsteps,
             "us_per_rve_iteration": res_ms * 1e3 / max(apps, 1.0),
             "cluster": info,
@@ -477,7 +488,7 @@ def run_b200_workload(M, env: Env, name: str, ngp: int, steps: int, warmup: int,
                   "assembled_equivalent_gbs": spmv_bytes_per_rve(n)[0] * h_apps / (max(h_ms, 1e-9) * 1e-3) / 1e9}
         apps = float(prof["spmv_slot_apps"])
     if res_info is not None and res_ms > 0.0:
-        roof = resident_roofline(n, res_info, res_ms, prof, prof_dev_ms, apps, steps, ngp)
+        roof = resident_roofline(n, res_info, res_ms, prof, prof_dev_ms, apps, steps, ngp, name)
     else:
         roof = spmv_roofline(name, n, prof, prof_dev_ms, apps, imp_kernel, steps,
                              vec_apps=apps + float(prof["hybrid_slot_apps"]))
