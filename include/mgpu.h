@@ -142,7 +142,8 @@ void mgpu_cg_resident(mgpu_ctx *, int which_list, int n);
 double mgpu_prof_resident_ms(mgpu_ctx *, int reset);
 float mgpu_bench_resident(mgpu_ctx *, int n, int reps, int dbg); /* isolated timing, see cg_resident.cu */
 void mgpu_resident_timeline(mgpu_ctx *, int slot, long long *out1024); /* per-warp phase cycles after a dbg-256 run */
-/* host-only replay of the plan of the cluster-resident kernel (CPU tests): see cg_resident.cu */
+/* host-only (CPU tests): see cg_resident.cu */
+int mgpu_resident_rows_sparse_host(const double *rows_pure /* [3][27][9] */);
 int mgpu_resident_replay_host(int nx, int ny, int nz, const int *elem_type, const double *rows_pure, const double *ke,
                               const double *p, double *Ap, int *meta8, int force_cs);
 void mgpu_axpy_u(mgpu_ctx *, int which_list, int n);

@@ -1304,6 +1304,17 @@ void mgpu_resident_timeline(mgpu_ctx *c, int slot, long long *out1024) {
                 cudaMemcpyDeviceToHost));
 }
 
+// Host-only: do the three pure-material row blocks rows[3][27][9] have the mirror-symmetry zero pattern that lets the
+// kernel run its 153-term operator copy (res_rows_sparse)?  (tests/test_resident_plan.py, no GPU)
+int mgpu_resident_rows_sparse_host(const double *rows_pure) {
+  PureRows R;
+  memset(&R, 0, sizeof(R));
+  for (int m = 0; m < 3; ++m)
+    for (int nbr = 0; nbr < 27; ++nbr)
+      for (int q = 0; q < 9; ++q) R.a[m * RB_LEN + nbr * RB_NBR + q] = rows_pure[((size_t)m * 27 + nbr) * 9 + q];
+  return res_rows_sparse(R) ? 1 : 0;
+}
+
 // Host-only replay of the plan (tests/test_resident_plan.py, no GPU): applies the operator to p exactly as the kernel
 // does -- per CTA a zeroed brick, own rows stored, halo rows delivered by res_push_dests, the chunk's pure-material row
 // block on every node of a chunk and res_fix_corr on the interface entries -- and returns Ap.  p / Ap: [3][nn]
@@ -1359,14 +1370,18 @@ int mgpu_resident_replay_host(int nx, int ny, int nz, const int *elem_type, cons
             brick[r][(size_t)d * G.cstride + lz * G.zp + ly * G.pitch + i0 + t] =
                 p[(size_t)d * nn + (size_t)k * nx * ny + j * nx + i0 + t];
     }
+  std::vector<int> incoming(G.cs, 0);
   for (int r = 0; r < G.cs; ++r)
     for (int k = 0; k < G.ntask[r]; ++k) {
       const int2 tk = plan.task[(size_t)r * G.taskcap + k];
       const int dr = (int)((unsigned)tk.y >> 24), doff = tk.y & 0xffffff;
       if (dr >= G.cs || dr == r) return -1;
+      incoming[dr] += 3 * nix * (int)sizeof(double);
       for (int d = 0; d < 3; ++d)
         for (int x = 0; x < nix; ++x) brick[dr][(size_t)d * G.cstride + doff + x] = brick[r][(size_t)d * G.cstride + tk.x + x];
     }
+  for (int r = 0; r < G.cs; ++r)  // the transaction count a CTA arms its halo mbarrier with = the bytes pushed to it
+    if (incoming[r] != G.halo_in[r]) return -6;
   for (int q = 0; q < 3 * nn; ++q) Ap[q] = 0.0;
   std::vector<int> written(nn, 0);
   for (int r = 0; r < G.cs; ++r)

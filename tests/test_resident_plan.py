@@ -118,3 +118,56 @@ def test_too_large_for_a_cluster(n):
     dims = (n, n, n)
     rc, _, _ = replay(dims, sphere_types(*dims), random_ke(np.random.default_rng(1)), np.zeros((3, n, n, n)))
     assert rc == 0
+
+
+def hex8_ke(E, nu, dx, dy, dz):
+    """24 x 24 stiffness of a hex8 element (2 x 2 x 2 Gauss points, isotropic material), node order of CX / CY / CZ."""
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    Cm = np.zeros((6, 6))
+    Cm[:3, :3] = lam
+    Cm[np.arange(3), np.arange(3)] += 2 * mu
+    Cm[np.arange(3, 6), np.arange(3, 6)] = mu
+    xi = np.array([[2 * CX[a] - 1, 2 * CY[a] - 1, 2 * CZ[a] - 1] for a in range(8)], dtype=float)
+    ke = np.zeros((24, 24))
+    g = 1 / np.sqrt(3.0)
+    for gx in (-g, g):
+        for gy in (-g, g):
+            for gz in (-g, g):
+                B = np.zeros((6, 24))
+                for a in range(8):
+                    dn = 0.125 * np.array([xi[a, 0] * (1 + xi[a, 1] * gy) * (1 + xi[a, 2] * gz) * 2 / dx,
+                                           xi[a, 1] * (1 + xi[a, 0] * gx) * (1 + xi[a, 2] * gz) * 2 / dy,
+                                           xi[a, 2] * (1 + xi[a, 0] * gx) * (1 + xi[a, 1] * gy) * 2 / dz])
+                    B[0, 3 * a], B[1, 3 * a + 1], B[2, 3 * a + 2] = dn
+                    B[3, 3 * a], B[3, 3 * a + 1] = dn[1], dn[0]
+                    B[4, 3 * a], B[4, 3 * a + 2] = dn[2], dn[0]
+                    B[5, 3 * a + 1], B[5, 3 * a + 2] = dn[2], dn[1]
+                ke += B.T @ Cm @ B * (dx * dy * dz / 8)
+    return ke
+
+
+def test_mirror_symmetry_pattern_of_pure_row_blocks():
+    """The 153-term operator copy of k_cg_resident rests on this: the ELL row block of a node surrounded by ONE isotropic
+    material on a regular grid couples components fi != fj only towards neighbours whose offset is non-zero along both
+    axes -- 90 of the 243 entries vanish (also for dx != dy != dz); a generic symmetric element matrix has no such
+    pattern and gets the dense copy."""
+    lib = M.load()
+    f = lib.mgpu_resident_rows_sparse_host
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(C.c_double)]
+    for dims in ((1.0, 1.0, 1.0), (0.3, 0.5, 0.2)):
+        ke = np.stack([hex8_ke(1e7, 0.3, *dims), hex8_ke(1e8, 0.25, *dims), hex8_ke(3e6, 0.2, *dims)])
+        rows = np.ascontiguousarray(pure_rows(ke))
+        nz = 0
+        for nbr in range(27):
+            o = (nbr % 3 - 1, (nbr // 3) % 3 - 1, nbr // 9 - 1)
+            for fi in range(3):
+                for fj in range(3):
+                    structural = fi == fj or (o[fi] != 0 and o[fj] != 0)
+                    nz += structural
+                    if not structural:
+                        assert abs(rows[:, nbr, fi * 3 + fj]).max() <= 1e-13 * abs(rows).max(), (nbr, fi, fj)
+        assert nz == 153
+        assert f(rows.ctypes.data_as(C.POINTER(C.c_double))) == 1
+    rows = np.ascontiguousarray(pure_rows(random_ke(np.random.default_rng(3))))
+    assert f(rows.ctypes.data_as(C.POINTER(C.c_double))) == 0
