@@ -274,7 +274,9 @@ def resident_roofline(n, info, res_ms, prof, prof_ms, apps, nsteps, ngp, name="e
     r_extra = {"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 48.0 * nn * ngp}
     return {**r_extra, "kernel": "k_cg_resident (whole DPCG solve: operator + dot products + vector updates of every iteration in "
                       "ONE launch, one thread-block cluster per RVE; no HBM traffic inside the loop)",
-            "bound": "fp64", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+            "bound": "fp64", "bound_detail": "FP64 DFMA pipe (vector units; BASELINE north_star: no tensor cores, FP64 "
+                                             "throughout); the HBM view of the same kernel is under `hbm`",
+            "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
             "peak_source": "nominal FP64: 148 SM x 64 DFMA/clk x 1965 MHz; a cluster of %d CTAs x %d clusters in flight "
                            "occupies %d of the 148 SMs" % (info["cs"], info["clusters"], info["cs"] * info["clusters"]),
             "flops_counted": "2 x 243 x interior nodes per DPCG iteration (the dense 27 x 3 x 3 stencil of SURVEY 8d); "
